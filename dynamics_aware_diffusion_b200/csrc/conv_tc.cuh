@@ -1,0 +1,329 @@
+// K1-K5: Conv1d-over-horizon as an implicit GEMM on the 5th-gen tensor cores (tcgen05), bf16 operands,
+// fp32 accumulation in TMEM, with the whole Conv1dBlock tail fused into the epilogue.
+//
+//   replaces  Conv1dBlock            nn.Conv1d(k,pad k//2) -> GroupNorm(8) -> Mish   temporal_unet.py:69-73
+//             + time-embedding add   out + time_mlp(t)[:, :, None]                   temporal_unet.py:117
+//             + residual add         out + residual_conv(x)                          temporal_unet.py:122
+//             Downsample1d / Upsample1d (two 2-tap phases) / 1x1 residual + head     temporal_unet.py:40,51,103,196
+//
+// GEMM view: rows m = (sample, position), M-tile = 128 rows = 128/L WHOLE samples, so GroupNorm
+// statistics never leave the CTA and the conv halo never crosses a tile; columns n = output
+// channels, N-tile a multiple of the GroupNorm group width; K = taps x input channels.
+//
+// A operand: a 4-D TMA tensor map (channel, stride-phase, position, sample) over the channels-last
+// bf16 activation.  For tap t the box is fetched at position offset tap_j[t]; positions outside
+// [0, L) are zero-filled by the TMA unit, which IS the convolution's zero padding.  The box lands in
+// shared memory as a 128 x 64 K-major tile with the 128-byte swizzle tcgen05 expects.
+// B operand: pre-packed bf16 weights Wb[n][tap * Cin + c] (K-major), 2-D TMA, same swizzle.
+//
+// Warp roles (192 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = TMEM allocator +
+// single-thread MMA issuer, warps 2-5 = epilogue (TMEM -> registers -> global).  Two TMEM
+// accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace dad {
+
+constexpr int TC_BM = 128;       // UMMA M (cta_group::1)
+constexpr int TC_BK = 64;        // bf16 elements per k-block = one 128 B swizzle row
+constexpr int TC_UMMA_K = 16;
+constexpr int TC_THREADS = 192;
+
+struct ConvTcParams {
+  const float *bias;             // [Cout_pad]
+  const float *gamma, *beta;     // GroupNorm affine (GN variants)
+  const float *ttab;             // [n_timesteps][Cout] time-bias table, or nullptr
+  const __nv_bfloat16 *residual; // (B, L_total, Cout) or nullptr
+  void *out;                     // bf16 (B, L_total, Cout), or fp32 (B, L_total, Cout) when out_f32
+  const LoopState *ls;
+  int B;                         // samples in this launch
+  int L_out;                     // rows per sample in the GEMM (divides 128)
+  int out_mul, out_phase;        // output row = l * out_mul + out_phase
+  int Cout;                      // real output channels (stores are clipped to it)
+  int n_tiles_m, n_tiles_n;
+  int kch1, kch2;                // 64-channel chunks of source 1 / source 2 (channel concat)
+  int taps;
+  int tap_j[kMaxTaps], tap_p[kMaxTaps];
+  int out_f32;
+};
+
+template <int BN>
+struct TcCfg {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;                 // 16 KB
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int B_ALLOC = (B_BYTES + 1023) / 1024 * 1024;
+  static constexpr int STAGE_BYTES = A_BYTES + B_ALLOC;
+  static constexpr int STAGES = (BN >= 256) ? 4 : 6;
+  static constexpr int ACC_STAGES = 2;
+  static constexpr int TMEM_COLS = (ACC_STAGES * BN <= 32) ? 32 : (ACC_STAGES * BN <= 64) ? 64
+                                   : (ACC_STAGES * BN <= 128) ? 128 : (ACC_STAGES * BN <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// GW = GroupNorm group width in columns (0: no GroupNorm/Mish, plain bias epilogue).
+template <int BN, int GW>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmW, const ConvTcParams p) {
+  using Cfg = TcCfg<BN>;
+  constexpr int CW = (BN < 32) ? 16 : 32;       // columns per TMEM load
+  constexpr int NCHUNK = BN / CW;
+  constexpr int NG = (GW > 0) ? BN / GW : 1;    // groups per N-tile
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t *empty_bar = full_bar + Cfg::STAGES;
+  uint64_t *tfull_bar = empty_bar + Cfg::STAGES;
+  uint64_t *tempty_bar = tfull_bar + Cfg::ACC_STAGES;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + Cfg::ACC_STAGES);
+  __shared__ float gn_scratch[2][4][2 * 8];     // [tile parity][epilogue warp][sum, sumsq per group]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.n_tiles_m * p.n_tiles_n;
+  const int kch = p.kch1 + p.kch2;
+  const int num_kb = p.taps * kch;
+  const int spt = TC_BM / p.L_out;              // samples per M-tile
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA1);
+    ptx::prefetch_tmap(&tmA2);
+    ptx::prefetch_tmap(&tmW);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < Cfg::ACC_STAGES; ++s) {
+      ptx::mbar_init(&tfull_bar[s], 1);
+      ptx::mbar_init(&tempty_bar[s], 4);        // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tm = tile / p.n_tiles_n, tn = tile - tm * p.n_tiles_n;
+        const int b0 = tm * spt, n0 = tn * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / kch, ch = kb - tap * kch;
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t *sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t *sb = sa + Cfg::A_BYTES;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+          if (ch < p.kch1) ptx::tma_load_4d(sa, &tmA1, &full_bar[stage], ch * TC_BK, p.tap_p[tap], p.tap_j[tap], b0);
+          else ptx::tma_load_4d(sa, &tmA2, &full_bar[stage], (ch - p.kch1) * TC_BK, p.tap_p[tap], p.tap_j[tap], b0);
+          ptx::tma_load_2d(sb, &tmW, &full_bar[stage], kb * TC_BK, n0);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(TC_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);   // epilogue has drained this accumulator
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);      // TMA bytes have landed
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t da = ptx::make_smem_desc_sw128(sa);
+          const uint64_t db = ptx::make_smem_desc_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+            // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in 16 B units
+            ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          ptx::umma_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tfull_bar[as]);               // accumulator complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================ epilogue ====================================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                  // row of the tile
+    const int s_in_tile = r / p.L_out;
+    const int l = r - s_in_tile * p.L_out;
+    const int L_total = p.L_out * p.out_mul;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int tm = tile / p.n_tiles_n, tn = tile - tm * p.n_tiles_n;
+      const int n0 = tn * BN;
+      const int b = tm * spt + s_in_tile;
+      const bool valid = b < p.B;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const uint32_t t_addr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+      ptx::mbar_wait(&tfull_bar[as], aphase);
+      ptx::tc_fence_after();
+
+      float mean[NG], rstd[NG];
+      if constexpr (GW > 0) {
+        // ---- pass 1: GroupNorm statistics of (conv + bias) over (L rows) x (GW columns)
+        float s1[NG], s2[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) { s1[g] = 0.f; s2[g] = 0.f; }
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+          uint32_t v[32];
+          if constexpr (CW == 32) ptx::tmem_ld32(t_addr + c * CW, v); else ptx::tmem_ld16(t_addr + c * CW, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < CW; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + c * CW + j));
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const float x = __uint_as_float(v[j + jj]) + bb[jj];
+              constexpr int dummy = 0; (void)dummy;
+              const int g = (c * CW + j + jj) / GW;   // compile-time after unrolling
+              s1[g] += x;
+              s2[g] = fmaf(x, x, s2[g]);
+            }
+          }
+        }
+        // reduce across the L rows of this sample (contiguous, aligned lanes)
+        const int lanes = p.L_out < 32 ? p.L_out : 32;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          for (int o = lanes >> 1; o > 0; o >>= 1) {
+            s1[g] += __shfl_xor_sync(0xffffffffu, s1[g], o);
+            s2[g] += __shfl_xor_sync(0xffffffffu, s2[g], o);
+          }
+        }
+        if (p.L_out > 32) {
+          // a sample spans several epilogue warps: combine through shared memory
+          float *scr = &gn_scratch[it & 1][0][0];
+          if (lane == 0) {
+#pragma unroll
+            for (int g = 0; g < NG; ++g) { scr[q * 16 + g] = s1[g]; scr[q * 16 + 8 + g] = s2[g]; }
+          }
+          ptx::named_bar_sync(1, 128);
+          const int wps = p.L_out / 32;
+          const int w0 = (q / wps) * wps;
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            float a = 0.f, c2 = 0.f;
+            for (int w = 0; w < wps; ++w) { a += scr[(w0 + w) * 16 + g]; c2 += scr[(w0 + w) * 16 + 8 + g]; }
+            s1[g] = a; s2[g] = c2;
+          }
+        }
+        const float inv_n = 1.0f / (float)(p.L_out * GW);
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          mean[g] = s1[g] * inv_n;
+          const float var = fmaxf(s2[g] * inv_n - mean[g] * mean[g], 0.f);
+          rstd[g] = rsqrtf(var + kGnEps);
+        }
+      }
+
+      // ---- pass 2: normalise, Mish, (+ time bias | + residual), convert, store
+      const float *trow = nullptr;
+      if (p.ttab) {
+        const long long t = p.ls->t_rows ? (valid ? p.ls->t_rows[b] : 0) : (long long)p.ls->step;
+        trow = p.ttab + (size_t)t * p.Cout + n0;
+      }
+      const size_t orow = ((size_t)b * L_total + (size_t)l * p.out_mul + p.out_phase) * p.Cout + n0;
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        uint32_t v[32];
+        if constexpr (CW == 32) ptx::tmem_ld32(t_addr + c * CW, v); else ptx::tmem_ld16(t_addr + c * CW, v);
+        ptx::tmem_ld_wait();
+        float y[CW];
+#pragma unroll
+        for (int j = 0; j < CW; j += 4) {
+          const int n = n0 + c * CW + j;
+          const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + n));
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+          if constexpr (GW > 0) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4 *>(p.gamma + n));
+            const float4 e4 = __ldg(reinterpret_cast<const float4 *>(p.beta + n));
+            const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int g = (c * CW + j + jj) / GW;
+              const float x = __uint_as_float(v[j + jj]) + bb[jj];
+              y[j + jj] = mish_fast((x - mean[g]) * rstd[g] * gg[jj] + ee[jj]);
+            }
+            if (trow) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4 *>(trow + c * CW + j));
+              y[j] += t4.x; y[j + 1] += t4.y; y[j + 2] += t4.z; y[j + 3] += t4.w;
+            }
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) y[j + jj] = __uint_as_float(v[j + jj]) + bb[jj];
+          }
+        }
+        if (valid) {
+          if (p.out_f32) {
+            float *o = reinterpret_cast<float *>(p.out) + orow + c * CW;
+#pragma unroll
+            for (int j = 0; j < CW; ++j)
+              if (n0 + c * CW + j < p.Cout) o[j] = y[j];
+          } else {
+            if (p.residual) {
+              const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + orow + c * CW);
+#pragma unroll
+              for (int j = 0; j < CW; j += 8) {
+                const uint4 rv = __ldg(rp + j / 8);
+                const __nv_bfloat162 *r2 = reinterpret_cast<const __nv_bfloat162 *>(&rv);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                  const float2 f = __bfloat1622float2(r2[jj]);
+                  y[j + 2 * jj] += f.x;
+                  y[j + 2 * jj + 1] += f.y;
+                }
+              }
+            }
+            uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + orow + c * CW);
+#pragma unroll
+            for (int j = 0; j < CW; j += 8) {
+              uint4 ov;
+              __nv_bfloat162 *o2 = reinterpret_cast<__nv_bfloat162 *>(&ov);
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) o2[jj] = __floats2bfloat162_rn(y[j + 2 * jj], y[j + 2 * jj + 1]);
+              op[j / 8] = ov;
+            }
+          }
+        }
+      }
+      // release the accumulator stage back to the MMA issuer
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace dad

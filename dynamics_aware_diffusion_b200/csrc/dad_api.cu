@@ -1,0 +1,1065 @@
+// C-ABI implementation (include/dad_b200.h): layer plan, weight re-packing, TMA descriptors,
+// CUDA-graph capture of one diffusion step, and the sampling loops.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "dad_b200.h"
+#include "common.cuh"
+#include "conv_tc.cuh"
+#include "kernels_f32.cuh"
+#include "step_kernel.cuh"
+
+using namespace dad;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Act {
+  size_t off;     // byte offset per sample
+  int L, C;       // rows per sample, stored channels
+};
+
+struct ConvOp {
+  std::string wname, bname, gname;  // state_dict stems: weight/bias of the conv, GroupNorm stem ("" = none)
+  int ksize = 1;
+  bool transposed = false;          // ConvTranspose1d weight layout (Cin, Cout, k)
+  TapSel sel{};                     // raw kernel index per packed tap
+  ConvGeom g{};                     // geometry with STORED channel counts
+  int Cin_real = 0, Cin_store = 0, Cout_pad = 0;
+  int in1 = -1, in2 = -1, out = -1, res = -1;
+  int tblock = -1;                  // index into time tables
+  bool head = false;
+  // device data
+  float *w_f32 = nullptr;
+  __nv_bfloat16 *w_b16 = nullptr;
+  float *bias = nullptr, *gamma = nullptr, *beta = nullptr;
+  // bf16 path
+  int BN = 0, GW = 0;
+  CUtensorMap tmA1, tmA2, tmW;
+  ConvTcParams tcp{};
+};
+
+struct TimeBlock {
+  std::string stem;   // "<block>.time_mlp.1"
+  int C = 0;
+  float *tab = nullptr;  // [S][C]
+};
+
+struct GraphEntry {
+  cudaGraphExec_t exec = nullptr;
+  long long kernels = 0;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct dad_handle {
+  dad_config cfg{};
+  std::string err;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  bool bf16 = false;
+  int time_dim = 0, D = 0, Cpad_in = 0;
+  size_t elt = 4;                    // activation element size
+  std::vector<Act> acts;
+  size_t act_bytes_per_sample = 0;
+  std::vector<ConvOp> ops;
+  std::vector<TimeBlock> tblocks;
+  std::vector<void *> allocs;        // everything freed in destroy
+  char *arena = nullptr;
+  float *d_eps = nullptr, *d_xtmp = nullptr;
+  LoopState *d_ls = nullptr;
+  float *d_sched[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool have_weights = false, have_sched = false;
+  // projector
+  float *d_Nt = nullptr, *d_Nrow = nullptr, *d_q = nullptr, *d_alpha = nullptr;
+  int projD = 0;
+  // conditions
+  int n_cond = 0, cond_per_batch = 0, cond_B = 0;
+  int cond_h[kMaxCond] = {0};
+  float *d_cond = nullptr;
+  size_t cond_cap = 0;
+  // host-buffer path
+  float *d_hostx = nullptr, *d_hostnoise = nullptr;
+  size_t hostx_cap = 0, hostnoise_cap = 0;
+  cudaStream_t cap_stream = nullptr, own_stream = nullptr;
+  std::map<long long, GraphEntry> graphs;
+  long long launches = 0;            // total kernels launched
+  long long counting = 0;            // kernels enqueued since last reset (capture accounting)
+  EncodeTiledFn encode = nullptr;
+  int64_t conv_flops = 0;
+};
+
+namespace {
+
+#define DAD_FAIL(h, code, ...)                              \
+  do {                                                      \
+    char _b[512];                                           \
+    snprintf(_b, sizeof(_b), __VA_ARGS__);                  \
+    (h)->err = _b;                                          \
+    return (code);                                          \
+  } while (0)
+
+#define CK(h, call)                                                                              \
+  do {                                                                                           \
+    cudaError_t _e = (call);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      DAD_FAIL(h, DAD_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+int dev_alloc(dad_handle *h, T **p, size_t n) {
+  void *q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(n * sizeof(T), 16));
+  if (e != cudaSuccess) DAD_FAIL(h, DAD_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+  h->allocs.push_back(q);
+  *p = reinterpret_cast<T *>(q);
+  return DAD_OK;
+}
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+int new_act(dad_handle *h, int L, int C) {
+  Act a;
+  a.off = h->act_bytes_per_sample;
+  a.L = L;
+  a.C = C;
+  size_t bytes = (size_t)L * C * h->elt;
+  bytes = (bytes + 255) / 256 * 256;
+  h->act_bytes_per_sample += bytes;
+  h->acts.push_back(a);
+  return (int)h->acts.size() - 1;
+}
+
+void *act_ptr(const dad_handle *h, int id) {
+  // activations are laid out act-major: [act][sample][L][C]; offset scales with the capacity
+  return h->arena + h->acts[id].off * (size_t)h->cfg.max_batch;
+}
+
+// ---- plan ------------------------------------------------------------------------------------
+// conv over `in1 (+ in2)` with `ksize` taps, stride 1, 'same' padding
+int add_conv(dad_handle *h, const std::string &stem, int in1, int in2, int Cin_real, int Cout, int L, int ksize,
+             const std::string &gn_stem, int tblock, int res) {
+  ConvOp op;
+  op.wname = stem + ".weight";
+  op.bname = stem + ".bias";
+  op.gname = gn_stem;
+  op.ksize = ksize;
+  op.g.C1 = h->acts[in1].C;
+  op.g.C2 = in2 >= 0 ? h->acts[in2].C : 0;
+  op.g.Cout = Cout;
+  op.g.taps = ksize;
+  for (int t = 0; t < ksize; ++t) {
+    op.g.tap_off[t] = t - ksize / 2;
+    op.sel.k[t] = t;
+  }
+  op.g.in_stride = 1;
+  op.g.L_in = L;
+  op.g.L_out = L;
+  op.g.out_mul = 1;
+  op.g.out_phase = 0;
+  op.Cin_real = Cin_real;
+  op.Cin_store = op.g.C1 + op.g.C2;
+  op.in1 = in1;
+  op.in2 = in2;
+  op.out = new_act(h, L, Cout);
+  op.res = res;
+  op.tblock = tblock;
+  h->ops.push_back(op);
+  return op.out;
+}
+
+int add_time_block(dad_handle *h, const std::string &stem, int C) {
+  TimeBlock tb;
+  tb.stem = stem;
+  tb.C = C;
+  h->tblocks.push_back(tb);
+  return (int)h->tblocks.size() - 1;
+}
+
+// ResidualTemporalBlock (temporal_unet.py:79-122)
+int add_res_block(dad_handle *h, const std::string &name, int in1, int in2, int Cin_real, int Cout, int L) {
+  const int ks = h->cfg.kernel_size;
+  const int tb = add_time_block(h, name + ".time_mlp.1", Cout);
+  const int h1 = add_conv(h, name + ".blocks.0.block.0", in1, in2, Cin_real, Cout, L, ks, name + ".blocks.0.block.1", tb, -1);
+  int r = in1;
+  if (Cin_real != Cout) r = add_conv(h, name + ".residual_conv", in1, in2, Cin_real, Cout, L, 1, "", -1, -1);
+  return add_conv(h, name + ".blocks.1.block.0", h1, -1, Cout, Cout, L, ks, name + ".blocks.1.block.1", -1, r);
+}
+
+int build_plan(dad_handle *h) {
+  const dad_config &c = h->cfg;
+  const int T = c.transition_dim;
+  int L = c.horizon;
+  h->Cpad_in = (T + 63) / 64 * 64;
+  const int x_act = new_act(h, L, h->bf16 ? h->Cpad_in : T);
+  int cur = x_act, curC = T;
+  std::vector<int> skips, skipC;
+  char nm[128];
+  for (int lvl = 0; lvl < c.n_levels; ++lvl) {
+    const int Co = c.dim * c.dim_mults[lvl];
+    snprintf(nm, sizeof(nm), "downs.%d.0", lvl);
+    cur = add_res_block(h, nm, cur, -1, curC, Co, L);
+    snprintf(nm, sizeof(nm), "downs.%d.1", lvl);
+    cur = add_res_block(h, nm, cur, -1, Co, Co, L);
+    curC = Co;
+    skips.push_back(cur);
+    skipC.push_back(Co);
+    if (lvl < c.n_levels - 1) {
+      // Downsample1d: Conv1d k3 s2 p1 (temporal_unet.py:40)
+      ConvOp op;
+      snprintf(nm, sizeof(nm), "downs.%d.2.conv", lvl);
+      op.wname = std::string(nm) + ".weight";
+      op.bname = std::string(nm) + ".bias";
+      op.ksize = 3;
+      op.g.C1 = h->acts[cur].C; op.g.C2 = 0; op.g.Cout = Co; op.g.taps = 3;
+      for (int t = 0; t < 3; ++t) { op.g.tap_off[t] = t - 1; op.sel.k[t] = t; }
+      op.g.in_stride = 2; op.g.L_in = L; op.g.L_out = L / 2; op.g.out_mul = 1; op.g.out_phase = 0;
+      op.Cin_real = Co; op.Cin_store = Co; op.in1 = cur; op.out = new_act(h, L / 2, Co);
+      h->ops.push_back(op);
+      cur = op.out;
+      L /= 2;
+    }
+  }
+  cur = add_res_block(h, "mid_block1", cur, -1, curC, curC, L);
+  cur = add_res_block(h, "mid_block2", cur, -1, curC, curC, L);
+  for (int u = 0; u < c.n_levels - 1; ++u) {
+    // ups[u] built from reversed(in_out[1:]) (temporal_unet.py:184-192): (dim_in, dim_out) = level n-2-u -> n-1-u
+    const int lvl_out = c.n_levels - 1 - u;
+    const int d_out = c.dim * c.dim_mults[lvl_out], d_in = c.dim * c.dim_mults[lvl_out - 1];
+    const int skip = skips.back();
+    skips.pop_back();
+    snprintf(nm, sizeof(nm), "ups.%d.0", u);
+    cur = add_res_block(h, nm, cur, skip, 2 * d_out, d_in, L);       // cat([x, h.pop()]) (:230)
+    snprintf(nm, sizeof(nm), "ups.%d.1", u);
+    cur = add_res_block(h, nm, cur, -1, d_in, d_in, L);
+    // Upsample1d: ConvTranspose1d k4 s2 p1 (:51) as two 2-tap phases.
+    //   even o=2j  : x[j-1] W[:,:,3] + x[j]   W[:,:,1]
+    //   odd  o=2j+1: x[j]   W[:,:,2] + x[j+1] W[:,:,0]
+    const int up_out = new_act(h, 2 * L, d_in);
+    for (int ph = 0; ph < 2; ++ph) {
+      ConvOp op;
+      snprintf(nm, sizeof(nm), "ups.%d.2.conv", u);
+      op.wname = std::string(nm) + ".weight";
+      op.bname = std::string(nm) + ".bias";
+      op.ksize = 4;
+      op.transposed = true;
+      op.g.C1 = h->acts[cur].C; op.g.C2 = 0; op.g.Cout = d_in; op.g.taps = 2;
+      if (ph == 0) { op.g.tap_off[0] = -1; op.sel.k[0] = 3; op.g.tap_off[1] = 0; op.sel.k[1] = 1; }
+      else         { op.g.tap_off[0] = 0;  op.sel.k[0] = 2; op.g.tap_off[1] = 1; op.sel.k[1] = 0; }
+      op.g.in_stride = 1; op.g.L_in = L; op.g.L_out = L; op.g.out_mul = 2; op.g.out_phase = ph;
+      op.Cin_real = d_in; op.Cin_store = d_in; op.in1 = cur; op.out = up_out;
+      h->ops.push_back(op);
+    }
+    cur = up_out;
+    curC = d_in;
+    L *= 2;
+  }
+  (void)skipC;
+  // final_conv: Conv1dBlock(dim, dim, k) -> Conv1d(dim, T, 1) (:194-197)
+  cur = add_conv(h, "final_conv.0.block.0", cur, -1, c.dim, c.dim, L, c.kernel_size, "final_conv.0.block.1", -1, -1);
+  {
+    ConvOp op;
+    op.wname = "final_conv.1.weight";
+    op.bname = "final_conv.1.bias";
+    op.ksize = 1;
+    op.g.C1 = h->acts[cur].C; op.g.C2 = 0; op.g.Cout = T; op.g.taps = 1; op.g.tap_off[0] = 0; op.sel.k[0] = 0;
+    op.g.in_stride = 1; op.g.L_in = L; op.g.L_out = L; op.g.out_mul = 1; op.g.out_phase = 0;
+    op.Cin_real = c.dim; op.Cin_store = c.dim; op.in1 = cur; op.out = -1; op.head = true;
+    h->ops.push_back(op);
+  }
+  if (L != c.horizon) DAD_FAIL(h, DAD_ERR_INVALID, "internal: decoder length %d != horizon %d", L, c.horizon);
+  h->conv_flops = 0;
+  for (const ConvOp &op : h->ops)
+    h->conv_flops += 2LL * op.g.L_out * op.g.taps * op.Cin_real * op.g.Cout;
+  return DAD_OK;
+}
+
+// ---- bf16 path set-up --------------------------------------------------------------------------
+int make_tmap(dad_handle *h, CUtensorMap *m, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
+              const cuuint32_t *box) {
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) DAD_FAIL(h, DAD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return DAD_OK;
+}
+
+int make_act_tmap(dad_handle *h, CUtensorMap *m, int act, const ConvGeom &g) {
+  const Act &a = h->acts[act];
+  const int P = g.in_stride, J = a.L / P;
+  cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)P, (cuuint64_t)J, (cuuint64_t)h->cfg.max_batch};
+  cuuint64_t strides[3] = {(cuuint64_t)a.C * 2, (cuuint64_t)P * a.C * 2, (cuuint64_t)a.L * a.C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BK, 1, (cuuint32_t)g.L_out, (cuuint32_t)(TC_BM / g.L_out)};
+  return make_tmap(h, m, act_ptr(h, act), 4, dims, strides, box);
+}
+
+int setup_tc_op(dad_handle *h, ConvOp &op) {
+  const ConvGeom &g = op.g;
+  if (g.L_out > TC_BM || TC_BM % g.L_out != 0)
+    DAD_FAIL(h, DAD_ERR_INVALID, "bf16 mode needs every level length to divide 128 (got %d); use fp32 mode", g.L_out);
+  if (g.C1 % TC_BK || g.C2 % TC_BK)
+    DAD_FAIL(h, DAD_ERR_INVALID, "bf16 mode needs channel counts that are multiples of 64 (got %d,%d); use fp32 mode", g.C1, g.C2);
+  if (op.head) {
+    op.GW = 0;
+    op.BN = g.Cout <= 16 ? 16 : g.Cout <= 32 ? 32 : g.Cout <= 64 ? 64 : 128;
+    if (g.Cout > 128) DAD_FAIL(h, DAD_ERR_INVALID, "bf16 mode supports transition_dim <= 128 (got %d)", g.Cout);
+  } else if (!op.gname.empty()) {
+    const int gw = g.Cout / kGroups;
+    if (g.Cout % kGroups) DAD_FAIL(h, DAD_ERR_INVALID, "channels %d not divisible by 8 groups", g.Cout);
+    if (gw == 8 && g.Cout == 64) { op.BN = 64; op.GW = 8; }
+    else if ((gw == 16 || gw == 32 || gw == 64 || gw == 128) && g.Cout % 128 == 0) { op.BN = 128; op.GW = gw; }
+    else if (gw == 256) { op.BN = 256; op.GW = 256; }
+    else DAD_FAIL(h, DAD_ERR_INVALID, "bf16 mode: unsupported GroupNorm width %d for %d channels; use fp32 mode", gw, g.Cout);
+  } else {
+    op.GW = 0;
+    if (g.Cout % 128 == 0) op.BN = 128;
+    else if (g.Cout % 64 == 0) op.BN = 64;
+    else DAD_FAIL(h, DAD_ERR_INVALID, "bf16 mode: unsupported channel count %d; use fp32 mode", g.Cout);
+  }
+  op.Cout_pad = cdiv(g.Cout, op.BN) * op.BN;
+  ConvTcParams &p = op.tcp;
+  p.L_out = g.L_out;
+  p.out_mul = g.out_mul;
+  p.out_phase = g.out_phase;
+  p.Cout = g.Cout;
+  p.n_tiles_n = op.Cout_pad / op.BN;
+  p.kch1 = g.C1 / TC_BK;
+  p.kch2 = g.C2 / TC_BK;
+  p.taps = g.taps;
+  for (int t = 0; t < g.taps; ++t) {
+    const int s = g.in_stride, off = g.tap_off[t];
+    const int ph = ((off % s) + s) % s;
+    p.tap_p[t] = ph;
+    p.tap_j[t] = (off - ph) / s;
+  }
+  p.out_f32 = op.head ? 1 : 0;
+  p.ls = h->d_ls;
+  return DAD_OK;
+}
+
+int finish_tc_op(dad_handle *h, ConvOp &op) {
+  // tensor maps need the final arena / weight addresses
+  int rc = make_act_tmap(h, &op.tmA1, op.in1, op.g);
+  if (rc) return rc;
+  rc = make_act_tmap(h, &op.tmA2, op.in2 >= 0 ? op.in2 : op.in1, op.g);
+  if (rc) return rc;
+  const cuuint64_t K = (cuuint64_t)op.g.taps * op.Cin_store;
+  cuuint64_t dims[2] = {K, (cuuint64_t)op.Cout_pad};
+  cuuint64_t strides[1] = {K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)op.BN};
+  rc = make_tmap(h, &op.tmW, op.w_b16, 2, dims, strides, box);
+  if (rc) return rc;
+  ConvTcParams &p = op.tcp;
+  p.bias = op.bias;
+  p.gamma = op.gamma;
+  p.beta = op.beta;
+  p.ttab = op.tblock >= 0 ? h->tblocks[op.tblock].tab : nullptr;
+  p.residual = op.res >= 0 ? reinterpret_cast<const __nv_bfloat16 *>(act_ptr(h, op.res)) : nullptr;
+  p.out = op.head ? (void *)h->d_eps : act_ptr(h, op.out);
+  return DAD_OK;
+}
+
+template <int BN, int GW>
+int launch_tc(dad_handle *h, const ConvOp &op, const ConvTcParams &p, int grid, cudaStream_t st) {
+  auto kern = conv_tc_kernel<BN, GW>;
+  kern<<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(op.tmA1, op.tmA2, op.tmW, p);
+  return DAD_OK;
+}
+
+template <int BN, int GW>
+cudaError_t set_tc_attr() {
+  return cudaFuncSetAttribute(conv_tc_kernel<BN, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES);
+}
+
+// Opt-in shared memory sizes are set once at create (never inside a stream capture).
+int set_kernel_attrs(dad_handle *h) {
+  CK(h, (set_tc_attr<64, 8>()));
+  CK(h, (set_tc_attr<128, 16>()));
+  CK(h, (set_tc_attr<128, 32>()));
+  CK(h, (set_tc_attr<128, 64>()));
+  CK(h, (set_tc_attr<128, 128>()));
+  CK(h, (set_tc_attr<256, 256>()));
+  CK(h, (set_tc_attr<16, 0>()));
+  CK(h, (set_tc_attr<32, 0>()));
+  CK(h, (set_tc_attr<64, 0>()));
+  CK(h, (set_tc_attr<128, 0>()));
+  CK(h, cudaFuncSetAttribute(step_project_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  return DAD_OK;
+}
+
+int enqueue_tc(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
+  ConvTcParams p = op.tcp;
+  p.B = B;
+  p.n_tiles_m = cdiv((long long)B * op.g.L_out, TC_BM);
+  const int tiles = p.n_tiles_m * p.n_tiles_n;
+  const int grid = std::min(tiles, h->sm_count);
+  int rc = DAD_ERR_INVALID;
+#define TC_CASE(bn, gw) if (op.BN == bn && op.GW == gw) rc = launch_tc<bn, gw>(h, op, p, grid, st);
+  TC_CASE(64, 8) TC_CASE(128, 16) TC_CASE(128, 32) TC_CASE(128, 64) TC_CASE(128, 128) TC_CASE(256, 256)
+  TC_CASE(16, 0) TC_CASE(32, 0) TC_CASE(64, 0) TC_CASE(128, 0)
+#undef TC_CASE
+  if (rc == DAD_ERR_INVALID) DAD_FAIL(h, DAD_ERR_INVALID, "internal: no tcgen05 instantiation for BN=%d GW=%d", op.BN, op.GW);
+  h->counting += 1;
+  return rc;
+}
+
+// ---- fp32 path ---------------------------------------------------------------------------------
+int enqueue_f32(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
+  ConvF32Params p{};
+  p.in1 = reinterpret_cast<const float *>(act_ptr(h, op.in1));
+  p.in2 = op.in2 >= 0 ? reinterpret_cast<const float *>(act_ptr(h, op.in2)) : nullptr;
+  p.w = op.w_f32;
+  p.bias = op.bias;
+  const bool gn = !op.gname.empty();
+  // with GroupNorm the residual is added after Mish (in the GN kernel), otherwise here
+  p.residual = (!gn && op.res >= 0) ? reinterpret_cast<const float *>(act_ptr(h, op.res)) : nullptr;
+  p.out = op.head ? h->d_eps : reinterpret_cast<float *>(act_ptr(h, op.out));
+  p.g = op.g;
+  p.B = B;
+  const bool vec = (op.g.C1 % 4 == 0) && (op.g.C2 % 4 == 0) && (op.g.Cout % 4 == 0);
+  dim3 grid(cdiv((long long)B * op.g.L_out, F32_BM), cdiv(op.g.Cout, F32_BN));
+  if (vec) conv_f32_kernel<EPI_BIAS, true><<<grid, 256, 0, st>>>(p);
+  else conv_f32_kernel<EPI_BIAS, false><<<grid, 256, 0, st>>>(p);
+  h->counting += 1;
+  if (gn) {
+    GnF32Params q{};
+    q.in = p.out;
+    q.out = p.out;
+    q.gamma = op.gamma;
+    q.beta = op.beta;
+    q.ttab = op.tblock >= 0 ? h->tblocks[op.tblock].tab : nullptr;
+    q.residual = op.res >= 0 ? reinterpret_cast<const float *>(act_ptr(h, op.res)) : nullptr;
+    q.ls = h->d_ls;
+    q.L = op.g.L_out;
+    q.C = op.g.Cout;
+    gn_mish_f32_kernel<<<dim3(B, kGroups), 128, 0, st>>>(q);
+    h->counting += 1;
+  }
+  return DAD_OK;
+}
+
+// One U-Net forward of the staged trajectories -> d_eps.  (TemporalUnet.forward, temporal_unet.py:199-241)
+int enqueue_unet(dad_handle *h, int B, cudaStream_t st) {
+  const dad_config &c = h->cfg;
+  const size_t rows = (size_t)B * c.horizon;
+  if (h->bf16) {
+    const size_t n = rows * h->Cpad_in;
+    stage_x_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->d_ls, nullptr, reinterpret_cast<__nv_bfloat16 *>(act_ptr(h, 0)), rows,
+                                                 c.transition_dim, h->Cpad_in);
+  } else {
+    const size_t n = rows * c.transition_dim;
+    stage_x_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->d_ls, reinterpret_cast<float *>(act_ptr(h, 0)), nullptr, rows,
+                                                 c.transition_dim, 0);
+  }
+  h->counting += 1;
+  for (const ConvOp &op : h->ops) {
+    int rc = h->bf16 ? enqueue_tc(h, op, B, st) : enqueue_f32(h, op, B, st);
+    if (rc) return rc;
+  }
+  CK(h, cudaGetLastError());
+  return DAD_OK;
+}
+
+// The fused remainder of the step (K7 [+ K8 for large D]).
+int enqueue_step(dad_handle *h, const float *model_out, int B, bool project, bool advance, cudaStream_t st) {
+  const dad_config &c = h->cfg;
+  StepParams p{};
+  p.ls = h->d_ls;
+  p.model_out = model_out;
+  p.xtmp = h->d_xtmp;
+  p.sqrt_recip = h->d_sched[0];
+  p.sqrt_recipm1 = h->d_sched[1];
+  p.coef1 = h->d_sched[2];
+  p.coef2 = h->d_sched[3];
+  p.logvar = h->d_sched[4];
+  p.alpha_tab = h->d_alpha;
+  p.Nt = h->d_Nt;
+  p.q = h->d_q;
+  p.cond_vals = h->d_cond;
+  p.B = B;
+  p.D = h->D;
+  p.T = c.transition_dim;
+  p.predict_epsilon = c.predict_epsilon;
+  p.clip_denoised = c.clip_denoised;
+  const size_t total4 = (size_t)B * h->D / 4;
+  if (!project) {
+    p.to_tmp = 0;
+    const int grid = (int)std::min<size_t>(cdiv(total4, 256), (size_t)h->sm_count * 8);
+    step_pointwise_kernel<<<grid, 256, 0, st>>>(p);
+    h->counting += 1;
+  } else {
+    const size_t fused_smem = ((size_t)h->D * h->D + (size_t)h->D * STEP_SB + h->D) * sizeof(float);
+    if (fused_smem <= (size_t)h->max_smem_optin) {
+      const int grid = std::min(cdiv(B, STEP_SB), h->sm_count);
+      step_project_fused_kernel<<<grid, 256, fused_smem, st>>>(p);
+      h->counting += 1;
+    } else {
+      // large D: pointwise part to scratch, then the projector as a tiled GEMM whose epilogue
+      // blends, inpaints and writes x (K8).
+      p.to_tmp = 1;
+      const int grid = (int)std::min<size_t>(cdiv(total4, 256), (size_t)h->sm_count * 8);
+      step_pointwise_kernel<<<grid, 256, 0, st>>>(p);
+      ConvF32Params g{};
+      g.in1 = h->d_xtmp;
+      g.w = h->d_Nt;            // Nt[k][d] is exactly the [c][n] weight layout
+      g.bias = h->d_q;
+      g.g.C1 = h->D; g.g.C2 = 0; g.g.Cout = h->D; g.g.taps = 1; g.g.tap_off[0] = 0;
+      g.g.in_stride = 1; g.g.L_in = 1; g.g.L_out = 1; g.g.out_mul = 1; g.g.out_phase = 0;
+      g.B = B;
+      g.ls = h->d_ls;
+      g.alpha_tab = h->d_alpha;
+      g.cond_vals = h->d_cond;
+      g.T = c.transition_dim;
+      dim3 grid2(cdiv(B, F32_BM), cdiv(h->D, F32_BN));
+      conv_f32_kernel<EPI_PROJECT, true><<<grid2, 256, 0, st>>>(g);
+      h->counting += 2;
+    }
+  }
+  if (advance) {
+    advance_step_kernel<<<1, 1, 0, st>>>(h->d_ls);
+    h->counting += 1;
+  }
+  CK(h, cudaGetLastError());
+  return DAD_OK;
+}
+
+int set_loop_state(dad_handle *h, const LoopState &v, cudaStream_t st) {
+  set_loop_state_kernel<<<1, 1, 0, st>>>(h->d_ls, v);
+  h->launches += 1;
+  CK(h, cudaGetLastError());
+  return DAD_OK;
+}
+
+void fill_cond(const dad_handle *h, LoopState &ls, int row0) {
+  ls.n_cond = h->n_cond;
+  ls.cond_per_batch = h->cond_per_batch;
+  ls.cond_B = h->cond_B;
+  ls.cond_row0 = row0;
+  for (int i = 0; i < kMaxCond; ++i) ls.cond_h[i] = h->cond_h[i];
+}
+
+void drop_graphs(dad_handle *h) {
+  for (auto &kv : h->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  h->graphs.clear();
+}
+
+int get_graph(dad_handle *h, int B, bool project, GraphEntry **out) {
+  const long long key = (long long)B * 2 + (project ? 1 : 0);
+  auto it = h->graphs.find(key);
+  if (it != h->graphs.end()) { *out = &it->second; return DAD_OK; }
+  cudaGraph_t graph = nullptr;
+  h->counting = 0;
+  CK(h, cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+  int rc = enqueue_unet(h, B, h->cap_stream);
+  if (!rc) rc = enqueue_step(h, h->d_eps, B, project, true, h->cap_stream);
+  cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (e != cudaSuccess) DAD_FAIL(h, DAD_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+  GraphEntry ge;
+  ge.kernels = h->counting;
+  e = cudaGraphInstantiate(&ge.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) DAD_FAIL(h, DAD_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+  h->graphs[key] = ge;
+  *out = &h->graphs[key];
+  return DAD_OK;
+}
+
+struct NamedTensors {
+  std::unordered_map<std::string, const dad_tensor *> map;
+  const dad_tensor *get(const std::string &n) const {
+    auto it = map.find(n);
+    return it == map.end() ? nullptr : it->second;
+  }
+};
+
+// Returns a DEVICE pointer to the tensor's data: the caller's pointer if it already is device
+// memory, otherwise a staged copy in `stage`.
+int device_view(dad_handle *h, const dad_tensor *t, float *stage, const float **out) {
+  cudaPointerAttributes at{};
+  cudaError_t e = cudaPointerGetAttributes(&at, t->data);
+  if (e == cudaSuccess && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged)) {
+    *out = t->data;
+    return DAD_OK;
+  }
+  cudaGetLastError();
+  CK(h, cudaMemcpy(stage, t->data, t->numel * sizeof(float), cudaMemcpyDefault));
+  *out = stage;
+  return DAD_OK;
+}
+
+int check_dims(dad_handle *h, const dad_tensor *t, const std::string &name, long long want) {
+  if (!t) DAD_FAIL(h, DAD_ERR_INVALID, "missing tensor '%s' in state_dict", name.c_str());
+  if (t->numel != want)
+    DAD_FAIL(h, DAD_ERR_INVALID, "tensor '%s' has %lld elements, expected %lld", name.c_str(), (long long)t->numel, want);
+  return DAD_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int dad_abi_version(void) { return DAD_ABI_VERSION; }
+
+const char *dad_last_error(const dad_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int dad_create(const dad_config *cfg, dad_handle **out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return DAD_ERR_INVALID; }
+  *out = nullptr;
+  dad_handle *h = new dad_handle();
+  h->cfg = *cfg;
+  auto fail = [&](int code) { g_create_error = h->err; dad_destroy(h); return code; };
+  const dad_config &c = h->cfg;
+  if (c.abi_version != DAD_ABI_VERSION) { h->err = "ABI version mismatch"; return fail(DAD_ERR_INVALID); }
+  if (c.n_levels < 1 || c.n_levels > DAD_MAX_LEVELS || c.transition_dim < 1 || c.dim < 8 || c.dim % 8 ||
+      c.horizon < 1 || c.n_timesteps < 1 || c.max_batch < 1 || c.kernel_size < 1 || c.kernel_size > 7 ||
+      c.kernel_size % 2 == 0) {
+    h->err = "invalid configuration (levels/dims/horizon/kernel_size)";
+    return fail(DAD_ERR_INVALID);
+  }
+  if (c.horizon % (1 << (c.n_levels - 1))) {
+    h->err = "horizon must be divisible by 2^(n_levels-1) (the reference U-Net cannot concatenate its skips otherwise)";
+    return fail(DAD_ERR_INVALID);
+  }
+  if ((c.horizon * c.transition_dim) % 4) { h->err = "horizon * transition_dim must be a multiple of 4"; return fail(DAD_ERR_INVALID); }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    h->err = "no CUDA device: this library has no CPU fallback";
+    return fail(DAD_ERR_DEVICE);
+  }
+  if (c.device < 0 || c.device >= ndev) { h->err = "device ordinal out of range"; return fail(DAD_ERR_DEVICE); }
+  cudaDeviceProp prop{};
+  if (cudaGetDeviceProperties(&prop, c.device) != cudaSuccess) { h->err = "cudaGetDeviceProperties failed"; return fail(DAD_ERR_CUDA); }
+  if (prop.major != 10) {
+    char b[160];
+    snprintf(b, sizeof(b), "device %d is sm_%d%d; this library is built for sm_100a (B200) only", c.device, prop.major, prop.minor);
+    h->err = b;
+    return fail(DAD_ERR_DEVICE);
+  }
+  if (cudaSetDevice(c.device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return fail(DAD_ERR_CUDA); }
+  h->sm_count = prop.multiProcessorCount;
+  h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  h->bf16 = c.precision == DAD_PRECISION_BF16;
+  h->elt = h->bf16 ? 2 : 4;
+  h->time_dim = c.time_dim > 0 ? c.time_dim : c.dim;
+  h->D = c.horizon * c.transition_dim;
+  if (h->bf16) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) {
+      h->err = "cuTensorMapEncodeTiled not available from the driver";
+      return fail(DAD_ERR_CUDA);
+    }
+    h->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  int rc = build_plan(h);
+  if (rc) return fail(rc);
+  if ((rc = set_kernel_attrs(h))) return fail(rc);
+  if (cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    h->err = "cudaStreamCreate failed";
+    return fail(DAD_ERR_CUDA);
+  }
+  // workspaces
+  const size_t arena_bytes = h->act_bytes_per_sample * (size_t)c.max_batch;
+  if ((rc = dev_alloc(h, &h->arena, arena_bytes))) return fail(rc);
+  cudaMemset(h->arena, 0, arena_bytes);
+  if ((rc = dev_alloc(h, &h->d_eps, (size_t)c.max_batch * h->D))) return fail(rc);
+  if ((rc = dev_alloc(h, &h->d_xtmp, (size_t)c.max_batch * h->D))) return fail(rc);
+  if ((rc = dev_alloc(h, &h->d_ls, 1))) return fail(rc);
+  cudaMemset(h->d_ls, 0, sizeof(LoopState));
+  for (int i = 0; i < 5; ++i)
+    if ((rc = dev_alloc(h, &h->d_sched[i], (size_t)c.n_timesteps))) return fail(rc);
+  if ((rc = dev_alloc(h, &h->d_alpha, (size_t)c.n_timesteps))) return fail(rc);
+  cudaMemset(h->d_alpha, 0, sizeof(float) * c.n_timesteps);
+  h->cond_cap = (size_t)kMaxCond * c.transition_dim;
+  if ((rc = dev_alloc(h, &h->d_cond, h->cond_cap))) return fail(rc);
+  // per-op parameter storage
+  for (ConvOp &op : h->ops) {
+    if (h->bf16) {
+      if ((rc = setup_tc_op(h, op))) return fail(rc);
+      if ((rc = dev_alloc(h, &op.w_b16, (size_t)op.Cout_pad * op.g.taps * op.Cin_store))) return fail(rc);
+    } else {
+      op.Cout_pad = op.g.Cout;
+      if ((rc = dev_alloc(h, &op.w_f32, (size_t)op.g.taps * op.Cin_store * op.g.Cout))) return fail(rc);
+    }
+    if ((rc = dev_alloc(h, &op.bias, (size_t)op.Cout_pad))) return fail(rc);
+    cudaMemset(op.bias, 0, sizeof(float) * op.Cout_pad);
+    if (!op.gname.empty()) {
+      if ((rc = dev_alloc(h, &op.gamma, (size_t)op.g.Cout))) return fail(rc);
+      if ((rc = dev_alloc(h, &op.beta, (size_t)op.g.Cout))) return fail(rc);
+    }
+  }
+  for (TimeBlock &tb : h->tblocks)
+    if ((rc = dev_alloc(h, &tb.tab, (size_t)c.n_timesteps * tb.C))) return fail(rc);
+  if (h->bf16)
+    for (ConvOp &op : h->ops)
+      if ((rc = finish_tc_op(h, op))) return fail(rc);
+  if (cudaDeviceSynchronize() != cudaSuccess) { h->err = "device error during create"; return fail(DAD_ERR_CUDA); }
+  *out = h;
+  return DAD_OK;
+}
+
+int dad_destroy(dad_handle *h) {
+  if (!h) return DAD_OK;
+  cudaDeviceSynchronize();
+  drop_graphs(h);
+  for (void *p : h->allocs) cudaFree(p);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return DAD_OK;
+}
+
+int dad_load_weights(dad_handle *h, const dad_tensor *tensors, int32_t n) {
+  if (!h || !tensors) return DAD_ERR_INVALID;
+  const dad_config &c = h->cfg;
+  CK(h, cudaSetDevice(c.device));
+  NamedTensors nt;
+  size_t max_numel = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!tensors[i].name || !tensors[i].data) DAD_FAIL(h, DAD_ERR_INVALID, "tensor %d has a null name or pointer", i);
+    nt.map[tensors[i].name] = &tensors[i];
+    max_numel = std::max<size_t>(max_numel, (size_t)tensors[i].numel);
+  }
+  float *stage = nullptr;
+  CK(h, cudaMalloc(&stage, std::max<size_t>(max_numel, 16) * sizeof(float)));
+  int rc = DAD_OK;
+  auto done = [&](int code) { cudaFree(stage); return code; };
+  cudaStream_t st = h->own_stream;
+  // ---- convolutions
+  for (ConvOp &op : h->ops) {
+    const dad_tensor *w = nt.get(op.wname), *b = nt.get(op.bname);
+    if ((rc = check_dims(h, w, op.wname, (long long)op.g.Cout * op.Cin_real * op.ksize))) return done(rc);
+    if ((rc = check_dims(h, b, op.bname, op.g.Cout))) return done(rc);
+    const float *wd = nullptr;
+    if ((rc = device_view(h, w, stage, &wd))) return done(rc);
+    if (h->bf16) {
+      const size_t total = (size_t)op.Cout_pad * op.g.taps * op.Cin_store;
+      pack_w_bf16_kernel<<<cdiv(total, 256), 256, 0, st>>>(wd, op.w_b16, op.g.Cout, op.Cin_real, op.Cout_pad,
+                                                           op.Cin_store, op.ksize, op.g.taps, op.sel, op.transposed);
+    } else {
+      const size_t total = (size_t)op.g.taps * op.Cin_real * op.g.Cout;
+      pack_w_f32_kernel<<<cdiv(total, 256), 256, 0, st>>>(wd, op.w_f32, op.g.Cout, op.Cin_real, op.ksize, op.g.taps,
+                                                          op.sel, op.transposed);
+    }
+    CK(h, cudaStreamSynchronize(st));   // `stage` is reused by the next tensor
+    CK(h, cudaMemcpy(op.bias, b->data, sizeof(float) * op.g.Cout, cudaMemcpyDefault));
+    if (!op.gname.empty()) {
+      const dad_tensor *gw = nt.get(op.gname + ".weight"), *gb = nt.get(op.gname + ".bias");
+      if ((rc = check_dims(h, gw, op.gname + ".weight", op.g.Cout))) return done(rc);
+      if ((rc = check_dims(h, gb, op.gname + ".bias", op.g.Cout))) return done(rc);
+      CK(h, cudaMemcpy(op.gamma, gw->data, sizeof(float) * op.g.Cout, cudaMemcpyDefault));
+      CK(h, cudaMemcpy(op.beta, gb->data, sizeof(float) * op.g.Cout, cudaMemcpyDefault));
+    }
+  }
+  // ---- time tables: every step index, once (K6)
+  const int S = c.n_timesteps, dim = c.dim, td = h->time_dim;
+  if (dim / 2 < 2) DAD_FAIL(h, DAD_ERR_INVALID, "dim too small for the sinusoidal embedding");
+  float *emb = nullptr, *h1 = nullptr, *temb = nullptr;
+  CK(h, cudaMalloc(&emb, sizeof(float) * S * dim));
+  CK(h, cudaMalloc(&h1, sizeof(float) * S * td * 4));
+  CK(h, cudaMalloc(&temb, sizeof(float) * S * td));
+  auto done2 = [&](int code) { cudaFree(emb); cudaFree(h1); cudaFree(temb); return done(code); };
+  {
+    const dad_tensor *w1 = nt.get("time_mlp.1.weight"), *b1 = nt.get("time_mlp.1.bias");
+    const dad_tensor *w3 = nt.get("time_mlp.3.weight"), *b3 = nt.get("time_mlp.3.bias");
+    if ((rc = check_dims(h, w1, "time_mlp.1.weight", (long long)td * 4 * dim))) return done2(rc);
+    if ((rc = check_dims(h, b1, "time_mlp.1.bias", td * 4))) return done2(rc);
+    if ((rc = check_dims(h, w3, "time_mlp.3.weight", (long long)td * td * 4))) return done2(rc);
+    if ((rc = check_dims(h, b3, "time_mlp.3.bias", td))) return done2(rc);
+    float *bd = nullptr;
+    CK(h, cudaMalloc(&bd, sizeof(float) * td * 4));
+    sinusoid_table_kernel<<<cdiv((long long)S * (dim / 2), 256), 256, 0, st>>>(emb, S, dim);
+    const float *wd = nullptr;
+    if ((rc = device_view(h, w1, stage, &wd))) { cudaFree(bd); return done2(rc); }
+    cudaMemcpy(bd, b1->data, sizeof(float) * td * 4, cudaMemcpyDefault);
+    linear_rows_kernel<<<cdiv((long long)S * td * 4, 256), 256, 0, st>>>(emb, wd, bd, h1, S, dim, td * 4, 0, 1);
+    cudaStreamSynchronize(st);
+    if ((rc = device_view(h, w3, stage, &wd))) { cudaFree(bd); return done2(rc); }
+    cudaMemcpy(bd, b3->data, sizeof(float) * td, cudaMemcpyDefault);
+    linear_rows_kernel<<<cdiv((long long)S * td, 256), 256, 0, st>>>(h1, wd, bd, temb, S, td * 4, td, 0, 0);
+    cudaStreamSynchronize(st);
+    cudaFree(bd);
+  }
+  for (TimeBlock &tb : h->tblocks) {
+    const dad_tensor *w = nt.get(tb.stem + ".weight"), *b = nt.get(tb.stem + ".bias");
+    if ((rc = check_dims(h, w, tb.stem + ".weight", (long long)tb.C * td))) return done2(rc);
+    if ((rc = check_dims(h, b, tb.stem + ".bias", tb.C))) return done2(rc);
+    const float *wd = nullptr;
+    if ((rc = device_view(h, w, stage, &wd))) return done2(rc);
+    float *bd = nullptr;
+    CK(h, cudaMalloc(&bd, sizeof(float) * tb.C));
+    cudaMemcpy(bd, b->data, sizeof(float) * tb.C, cudaMemcpyDefault);
+    linear_rows_kernel<<<cdiv((long long)S * tb.C, 256), 256, 0, st>>>(temb, wd, bd, tb.tab, S, td, tb.C, 1, 0);
+    cudaStreamSynchronize(st);
+    cudaFree(bd);
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { h->err = std::string("weight packing failed: ") + cudaGetErrorString(e); return done2(DAD_ERR_CUDA); }
+  h->have_weights = true;
+  return done2(DAD_OK);
+}
+
+int dad_set_schedule(dad_handle *h, const float *sr, const float *srm1, const float *c1, const float *c2,
+                     const float *lv, int32_t n) {
+  if (!h || !sr || !srm1 || !c1 || !c2 || !lv) return DAD_ERR_INVALID;
+  if (n != h->cfg.n_timesteps) DAD_FAIL(h, DAD_ERR_INVALID, "schedule length %d != n_timesteps %d", n, h->cfg.n_timesteps);
+  CK(h, cudaSetDevice(h->cfg.device));
+  const float *src[5] = {sr, srm1, c1, c2, lv};
+  for (int i = 0; i < 5; ++i) CK(h, cudaMemcpy(h->d_sched[i], src[i], sizeof(float) * n, cudaMemcpyDefault));
+  h->have_sched = true;
+  return DAD_OK;
+}
+
+int dad_set_projector(dad_handle *h, const float *Nmat, const float *q, const float *alpha, int32_t D, int32_t n) {
+  if (!h) return DAD_ERR_INVALID;
+  CK(h, cudaSetDevice(h->cfg.device));
+  if (!Nmat) { h->projD = 0; return DAD_OK; }
+  if (!q || !alpha) return DAD_ERR_INVALID;
+  if (D != h->D) DAD_FAIL(h, DAD_ERR_INVALID, "projector dimension %d != horizon*transition_dim %d", D, h->D);
+  if (n != h->cfg.n_timesteps) DAD_FAIL(h, DAD_ERR_INVALID, "alpha length %d != n_timesteps %d", n, h->cfg.n_timesteps);
+  if (!h->d_Nt) {
+    int rc;
+    if ((rc = dev_alloc(h, &h->d_Nt, (size_t)D * D))) return rc;
+    if ((rc = dev_alloc(h, &h->d_Nrow, (size_t)D * D))) return rc;
+    if ((rc = dev_alloc(h, &h->d_q, (size_t)D))) return rc;
+    drop_graphs(h);   // new buffers -> captured pointers are stale
+  }
+  CK(h, cudaMemcpy(h->d_Nrow, Nmat, sizeof(float) * D * D, cudaMemcpyDefault));
+  CK(h, cudaMemcpy(h->d_q, q, sizeof(float) * D, cudaMemcpyDefault));
+  CK(h, cudaMemcpy(h->d_alpha, alpha, sizeof(float) * n, cudaMemcpyDefault));
+  // transpose on device via the fp32 packer: treat Nmat as a (Cout=D, Cin=D, k=1) conv weight -> [c][n]
+  TapSel sel{};
+  pack_w_f32_kernel<<<cdiv((long long)D * D, 256), 256, 0, h->own_stream>>>(h->d_Nrow, h->d_Nt, D, D, 1, 1, sel, 0);
+  CK(h, cudaStreamSynchronize(h->own_stream));
+  h->projD = D;
+  return DAD_OK;
+}
+
+int dad_set_conditions(dad_handle *h, const int32_t *h_idx, const float *vals, int32_t n_cond, int32_t per_batch,
+                       int32_t B) {
+  if (!h) return DAD_ERR_INVALID;
+  CK(h, cudaSetDevice(h->cfg.device));
+  if (n_cond <= 0) { h->n_cond = 0; return DAD_OK; }
+  if (!h_idx || !vals) return DAD_ERR_INVALID;
+  if (n_cond > kMaxCond) DAD_FAIL(h, DAD_ERR_INVALID, "at most %d conditions are supported (got %d)", kMaxCond, n_cond);
+  for (int i = 0; i < n_cond; ++i) {
+    int hh = h_idx[i];
+    if (hh < 0) hh += h->cfg.horizon;       // python-style negative index (e.g. {-1: goal})
+    if (hh < 0 || hh >= h->cfg.horizon) DAD_FAIL(h, DAD_ERR_INVALID, "condition index %d outside the horizon", h_idx[i]);
+    h->cond_h[i] = hh;
+  }
+  const size_t need = (size_t)n_cond * (per_batch ? B : 1) * h->cfg.transition_dim;
+  if (need > h->cond_cap) {
+    int rc;
+    if ((rc = dev_alloc(h, &h->d_cond, need))) return rc;
+    h->cond_cap = need;
+    drop_graphs(h);
+  }
+  CK(h, cudaMemcpy(h->d_cond, vals, sizeof(float) * need, cudaMemcpyDefault));
+  h->n_cond = n_cond;
+  h->cond_per_batch = per_batch ? 1 : 0;
+  h->cond_B = per_batch ? B : 1;
+  return DAD_OK;
+}
+
+int dad_unet_forward(dad_handle *h, const float *x, const int64_t *t, int32_t step, float *eps, int32_t B, void *stream) {
+  if (!h || !x || !eps || B < 1) return DAD_ERR_INVALID;
+  if (!h->have_weights) DAD_FAIL(h, DAD_ERR_STATE, "dad_unet_forward before dad_load_weights");
+  if (!t && (step < 0 || step >= h->cfg.n_timesteps)) DAD_FAIL(h, DAD_ERR_INVALID, "step %d outside [0, %d)", step, h->cfg.n_timesteps);
+  CK(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int c0 = 0; c0 < B; c0 += h->cfg.max_batch) {
+    const int Bc = std::min(h->cfg.max_batch, B - c0);
+    LoopState ls{};
+    ls.step = step;
+    ls.n_steps = step + 1;
+    ls.x = const_cast<float *>(x) + (size_t)c0 * h->D;
+    ls.t_rows = t ? reinterpret_cast<const long long *>(t) + c0 : nullptr;
+    int rc = set_loop_state(h, ls, st);
+    if (rc) return rc;
+    h->counting = 0;
+    if ((rc = enqueue_unet(h, Bc, st))) return rc;
+    h->launches += h->counting;
+    CK(h, cudaMemcpyAsync(eps + (size_t)c0 * h->D, h->d_eps, sizeof(float) * (size_t)Bc * h->D, cudaMemcpyDeviceToDevice, st));
+  }
+  return DAD_OK;
+}
+
+int dad_step(dad_handle *h, float *x, const float *model_out, const float *noise, const float *grad, float guide_w,
+             int32_t step, uint32_t flags, uint64_t seed, uint64_t sample_offset, int32_t B, void *stream) {
+  if (!h || !x || !model_out || B < 1) return DAD_ERR_INVALID;
+  if (!h->have_sched) DAD_FAIL(h, DAD_ERR_STATE, "dad_step before dad_set_schedule");
+  if (step < 0 || step >= h->cfg.n_timesteps) DAD_FAIL(h, DAD_ERR_INVALID, "step %d outside [0, %d)", step, h->cfg.n_timesteps);
+  const bool project = (flags & DAD_FLAG_PROJECT) != 0;
+  if (project && !h->projD) DAD_FAIL(h, DAD_ERR_STATE, "DAD_FLAG_PROJECT without dad_set_projector");
+  CK(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int c0 = 0; c0 < B; c0 += h->cfg.max_batch) {
+    const int Bc = std::min(h->cfg.max_batch, B - c0);
+    const size_t o = (size_t)c0 * h->D;
+    LoopState ls{};
+    ls.step = step;
+    ls.n_steps = step + 1;          // noise slot 0 == the tensor passed in
+    ls.flags = flags;
+    ls.guide_w = guide_w;
+    ls.x = x + o;
+    ls.noise = noise ? noise + o : nullptr;
+    ls.noise_stride = 0;
+    ls.grad = grad ? grad + o : nullptr;
+    ls.seed = seed;
+    ls.sample_offset = sample_offset + c0;
+    fill_cond(h, ls, c0);
+    int rc = set_loop_state(h, ls, st);
+    if (rc) return rc;
+    h->counting = 0;
+    if ((rc = enqueue_step(h, model_out + o, Bc, project, false, st))) return rc;
+    h->launches += h->counting;
+  }
+  return DAD_OK;
+}
+
+int dad_project(dad_handle *h, float *x, int32_t step, int32_t B, void *stream) {
+  if (!h || !x || B < 1) return DAD_ERR_INVALID;
+  if (!h->projD) DAD_FAIL(h, DAD_ERR_STATE, "dad_project without dad_set_projector");
+  if (step < 0 || step >= h->cfg.n_timesteps) DAD_FAIL(h, DAD_ERR_INVALID, "step %d outside [0, %d)", step, h->cfg.n_timesteps);
+  CK(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int c0 = 0; c0 < B; c0 += h->cfg.max_batch) {
+    const int Bc = std::min(h->cfg.max_batch, B - c0);
+    float *xc = x + (size_t)c0 * h->D;
+    // the GEMM reads whole rows while other CTAs write them: go through the scratch copy
+    CK(h, cudaMemcpyAsync(h->d_xtmp, xc, sizeof(float) * (size_t)Bc * h->D, cudaMemcpyDeviceToDevice, st));
+    LoopState ls{};
+    ls.step = step;
+    ls.n_steps = step + 1;
+    ls.x = xc;
+    int rc = set_loop_state(h, ls, st);
+    if (rc) return rc;
+    ConvF32Params g{};
+    g.in1 = h->d_xtmp;
+    g.w = h->d_Nt;
+    g.bias = h->d_q;
+    g.g.C1 = h->D; g.g.C2 = 0; g.g.Cout = h->D; g.g.taps = 1; g.g.tap_off[0] = 0;
+    g.g.in_stride = 1; g.g.L_in = 1; g.g.L_out = 1; g.g.out_mul = 1; g.g.out_phase = 0;
+    g.B = Bc;
+    g.ls = h->d_ls;
+    g.alpha_tab = h->d_alpha;
+    g.cond_vals = h->d_cond;
+    g.T = h->cfg.transition_dim;
+    dim3 grid(cdiv(Bc, F32_BM), cdiv(h->D, F32_BN));
+    conv_f32_kernel<EPI_PROJECT, true><<<grid, 256, 0, st>>>(g);
+    h->launches += 1;
+    CK(h, cudaGetLastError());
+  }
+  return DAD_OK;
+}
+
+int dad_sample(dad_handle *h, float *x, const float *noise_seq, uint64_t seed, uint64_t sample_offset, int32_t B,
+               int32_t n_steps, uint32_t flags, float *trace, void *stream) {
+  if (!h || !x || B < 1) return DAD_ERR_INVALID;
+  if (!h->have_weights || !h->have_sched) DAD_FAIL(h, DAD_ERR_STATE, "dad_sample before weights and schedule are set");
+  if (n_steps < 1 || n_steps > h->cfg.n_timesteps)
+    DAD_FAIL(h, DAD_ERR_INVALID, "n_steps %d outside [1, %d] (the schedule tables have n_timesteps entries)", n_steps, h->cfg.n_timesteps);
+  const bool project = (flags & DAD_FLAG_PROJECT) != 0;
+  if (project && !h->projD) DAD_FAIL(h, DAD_ERR_STATE, "DAD_FLAG_PROJECT without dad_set_projector");
+  if ((flags & DAD_FLAG_CONDITIONS) && h->n_cond && h->cond_per_batch && h->cond_B != B)
+    DAD_FAIL(h, DAD_ERR_INVALID, "per-batch conditions were registered for B=%d, sampling B=%d", h->cond_B, B);
+  CK(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t D = h->D;
+  for (int c0 = 0; c0 < B; c0 += h->cfg.max_batch) {
+    const int Bc = std::min(h->cfg.max_batch, B - c0);
+    LoopState ls{};
+    ls.step = n_steps - 1;
+    ls.n_steps = n_steps;
+    ls.flags = flags;
+    ls.x = x + (size_t)c0 * D;
+    ls.noise = noise_seq ? noise_seq + (size_t)c0 * D : nullptr;
+    ls.noise_stride = (long long)B * D;
+    ls.trace = trace ? trace + (size_t)c0 * D : nullptr;
+    ls.trace_stride = (long long)B * D;
+    ls.seed = seed;
+    ls.sample_offset = sample_offset + c0;
+    fill_cond(h, ls, c0);
+    int rc = set_loop_state(h, ls, st);
+    if (rc) return rc;
+    const bool draw = (flags & DAD_FLAG_PHILOX_INIT) != 0;
+    if (draw || ((flags & DAD_FLAG_CONDITIONS) && h->n_cond)) {
+      init_x_kernel<<<cdiv((size_t)Bc * D / 4, 256), 256, 0, st>>>(h->d_ls, h->d_cond, Bc, (int)D, h->cfg.transition_dim, draw ? 1 : 0);
+      h->launches += 1;
+    }
+    GraphEntry *ge = nullptr;
+    if ((rc = get_graph(h, Bc, project, &ge))) return rc;
+    for (int s = 0; s < n_steps; ++s) CK(h, cudaGraphLaunch(ge->exec, st));
+    h->launches += ge->kernels * n_steps;
+  }
+  return DAD_OK;
+}
+
+int dad_sample_host(dad_handle *h, float *x_host, const float *noise_seq_host, uint64_t seed, uint64_t sample_offset,
+                    int32_t B, int32_t n_steps, uint32_t flags) {
+  if (!h || !x_host || B < 1) return DAD_ERR_INVALID;
+  CK(h, cudaSetDevice(h->cfg.device));
+  const size_t n = (size_t)B * h->D;
+  if (n > h->hostx_cap) {
+    int rc;
+    if ((rc = dev_alloc(h, &h->d_hostx, n))) return rc;
+    h->hostx_cap = n;
+  }
+  const float *d_noise = nullptr;
+  if (noise_seq_host) {
+    const size_t nn = n * (size_t)n_steps;
+    if (nn > h->hostnoise_cap) {
+      int rc;
+      if ((rc = dev_alloc(h, &h->d_hostnoise, nn))) return rc;
+      h->hostnoise_cap = nn;
+    }
+    CK(h, cudaMemcpyAsync(h->d_hostnoise, noise_seq_host, sizeof(float) * nn, cudaMemcpyHostToDevice, h->own_stream));
+    d_noise = h->d_hostnoise;
+  }
+  if (!(flags & DAD_FLAG_PHILOX_INIT))
+    CK(h, cudaMemcpyAsync(h->d_hostx, x_host, sizeof(float) * n, cudaMemcpyHostToDevice, h->own_stream));
+  int rc = dad_sample(h, h->d_hostx, d_noise, seed, sample_offset, B, n_steps, flags, nullptr, h->own_stream);
+  if (rc) return rc;
+  CK(h, cudaMemcpyAsync(x_host, h->d_hostx, sizeof(float) * n, cudaMemcpyDeviceToHost, h->own_stream));
+  CK(h, cudaStreamSynchronize(h->own_stream));
+  return DAD_OK;
+}
+
+int dad_get_info(const dad_handle *h, dad_info *out) {
+  if (!h || !out) return DAD_ERR_INVALID;
+  out->conv_flops_per_sample = h->conv_flops;
+  long long per_step = 1;  // stage_x
+  for (const ConvOp &op : h->ops) per_step += (h->bf16 || op.gname.empty()) ? 1 : 2;
+  per_step += 2;           // fused step kernel + advance (projector GEMM adds one for large D)
+  out->launches_per_step = per_step;
+  out->workspace_bytes = (int64_t)(h->act_bytes_per_sample * (size_t)h->cfg.max_batch);
+  out->n_conv_layers = (int32_t)h->ops.size();
+  out->sm_count = h->sm_count;
+  return DAD_OK;
+}
+
+int64_t dad_launch_count(const dad_handle *h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,287 @@
+// fp32 SIMT kernels: the 1e-5 parity mode of the U-Net, the time-embedding tables and the
+// weight re-packers.  Everything is channels-last: activations (B, L, C).
+#pragma once
+#include "common.cuh"
+
+namespace dad {
+
+// ------------------------------------------------------------------------------------------
+// Implicit-GEMM Conv1d / ConvTranspose1d-phase / 1x1 conv, fp32 in, fp32 accumulate.
+//   replaces nn.Conv1d / nn.ConvTranspose1d calls at temporal_unet.py:40,51,70,103,196
+//   weights: Wp[tap][c][n]  (n contiguous).
+// Tile 64 rows x 64 cols x 16 k, 256 threads, 4x4 outputs per thread.
+// ------------------------------------------------------------------------------------------
+constexpr int F32_BM = 64, F32_BN = 64, F32_BK = 16;
+
+enum { EPI_BIAS = 0, EPI_PROJECT = 1 };
+
+struct ConvF32Params {
+  const float *in1, *in2;
+  const float *w;
+  const float *bias;
+  const float *residual;     // same layout as out, or nullptr
+  float *out;
+  ConvGeom g;
+  int B;
+  // EPI_PROJECT only
+  const LoopState *ls;
+  const float *alpha_tab;
+  const float *cond_vals;
+  int T;
+};
+
+template <int EPI, bool VEC>
+__global__ void __launch_bounds__(256) conv_f32_kernel(const ConvF32Params p) {
+  __shared__ float As[F32_BK][F32_BM + 4];
+  __shared__ float Bs[F32_BK][F32_BN];
+  const ConvGeom &g = p.g;
+  const int Cin = g.C1 + g.C2;
+  const int K = g.taps * Cin;
+  const int M = p.B * g.L_out;
+  const int m0 = blockIdx.x * F32_BM, n0 = blockIdx.y * F32_BN;
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+
+  // A loader: one row, 4 consecutive k per thread.
+  const int a_row = tid >> 2, a_k = (tid & 3) * 4;
+  const int am = m0 + a_row;
+  const bool a_ok = am < M;
+  const int ab = a_ok ? am / g.L_out : 0;
+  const int alo = a_ok ? am - ab * g.L_out : 0;
+  // B loader: one k, 4 consecutive n per thread.
+  const int b_k = tid >> 4, b_n = (tid & 15) * 4;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += F32_BK) {
+    // ---- A tile
+    float av[4] = {0.f, 0.f, 0.f, 0.f};
+    if (a_ok) {
+      const int kk = k0 + a_k;
+      if (VEC) {
+        if (kk < K) {
+          const int tap = kk / Cin, c = kk - tap * Cin;
+          const int li = alo * g.in_stride + g.tap_off[tap];
+          if (li >= 0 && li < g.L_in) {
+            const float *src = (c < g.C1) ? p.in1 + ((size_t)(ab * g.L_in + li) * g.C1 + c)
+                                          : p.in2 + ((size_t)(ab * g.L_in + li) * g.C2 + (c - g.C1));
+            const float4 v = *reinterpret_cast<const float4 *>(src);
+            av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kj = kk + j;
+          if (kj < K) {
+            const int tap = kj / Cin, c = kj - tap * Cin;
+            const int li = alo * g.in_stride + g.tap_off[tap];
+            if (li >= 0 && li < g.L_in)
+              av[j] = (c < g.C1) ? p.in1[(size_t)(ab * g.L_in + li) * g.C1 + c]
+                                 : p.in2[(size_t)(ab * g.L_in + li) * g.C2 + (c - g.C1)];
+          }
+        }
+      }
+    }
+    // ---- B tile
+    float bv[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+      const int kk = k0 + b_k, n = n0 + b_n;
+      if (kk < K) {
+        const float *src = p.w + (size_t)kk * g.Cout + n;
+        if (VEC && n + 3 < g.Cout) {
+          const float4 v = *reinterpret_cast<const float4 *>(src);
+          bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (n + j < g.Cout) bv[j] = src[j];
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) As[a_k + j][a_row] = av[j];
+    *reinterpret_cast<float4 *>(&Bs[b_k][b_n]) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < F32_BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+      const float ar[4] = {a.x, a.y, a.z, a.w}, br[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+  }
+
+  // ---- epilogue
+  float alpha = 0.f;
+  int n_cond = 0;
+  LoopState ls;
+  if (EPI == EPI_PROJECT) {
+    ls = *p.ls;
+    alpha = p.alpha_tab[ls.step];
+    n_cond = ((ls.flags & 1u) && !(ls.flags & 4u)) ? ls.n_cond : 0;  // project -> inpaint order
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const int b = m / g.L_out, lo = m - b * g.L_out;
+    const size_t orow = ((size_t)b * (g.L_out * g.out_mul) + lo * g.out_mul + g.out_phase) * g.Cout;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= g.Cout) continue;
+      float v = acc[i][j] + p.bias[n];
+      if (EPI == EPI_BIAS) {
+        if (p.residual) v += p.residual[orow + n];
+      } else {
+        // y = x + alpha * (N x + q), then Diffuser-style inpainting (policies.py:48-63).
+        v = p.in1[(size_t)m * g.C1 + n] + alpha * v;
+        const int hh = n / p.T, tt = n - hh * p.T;
+        for (int c = 0; c < n_cond; ++c)
+          if (ls.cond_h[c] == hh)
+            v = p.cond_vals[((size_t)c * (ls.cond_per_batch ? ls.cond_B : 1) +
+                             (ls.cond_per_batch ? (ls.cond_row0 + m) : 0)) * p.T + tt];
+        if (ls.trace) ls.trace[(size_t)(ls.n_steps - 1 - ls.step) * ls.trace_stride + orow + n] = v;
+      }
+      (EPI == EPI_PROJECT ? ls.x : p.out)[orow + n] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm(8) + Mish (+ time bias | + residual), fp32.  One block per (sample, group).
+//   temporal_unet.py:71-72 (GN, Mish), :117 (time add), :122 (residual add)
+// ------------------------------------------------------------------------------------------
+struct GnF32Params {
+  const float *in;
+  float *out;
+  const float *gamma, *beta;
+  const float *ttab;          // [n_timesteps][C] time-bias table or nullptr
+  const float *residual;      // (B, L, C) or nullptr
+  const LoopState *ls;
+  int L, C;
+};
+
+__global__ void __launch_bounds__(128) gn_mish_f32_kernel(const GnF32Params p) {
+  __shared__ float red[32];
+  const int b = blockIdx.x, grp = blockIdx.y;
+  const int gw = p.C / kGroups;
+  const int n = p.L * gw;
+  const float *src = p.in + (size_t)b * p.L * p.C + grp * gw;
+  float s = 0.f;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int l = e / gw, j = e - l * gw;
+    s += src[(size_t)l * p.C + j];
+  }
+  const float mean = block_sum(s, red) / (float)n;
+  float q = 0.f;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int l = e / gw, j = e - l * gw;
+    const float d = src[(size_t)l * p.C + j] - mean;
+    q += d * d;
+  }
+  const float var = block_sum(q, red) / (float)n;
+  const float rstd = 1.0f / sqrtf(var + kGnEps);
+  long long t = 0;
+  if (p.ttab) t = p.ls->t_rows ? p.ls->t_rows[b] : (long long)p.ls->step;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int l = e / gw, j = e - l * gw;
+    const int c = grp * gw + j;
+    const size_t idx = ((size_t)b * p.L + l) * p.C + c;
+    float v = (p.in[idx] - mean) * rstd * p.gamma[c] + p.beta[c];
+    v = mish_precise(v);
+    if (p.ttab) v += p.ttab[(size_t)t * p.C + c];
+    if (p.residual) v += p.residual[idx];
+    p.out[idx] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Time-embedding tables, computed once at load for every step index (K6).
+//   temporal_unet.py:26-32 (sinusoid), :155-160 (global MLP), :97-100 (per-block Mish + Linear)
+// ------------------------------------------------------------------------------------------
+__global__ void sinusoid_table_kernel(float *out, int S, int dim) {
+  const int half = dim / 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * half) return;
+  const int s = idx / half, j = idx - s * half;
+  const float scale = logf(10000.f) / (float)(half - 1);
+  const float f = expf((float)j * -scale);
+  const float a = (float)s * f;
+  out[(size_t)s * dim + j] = sinf(a);
+  out[(size_t)s * dim + half + j] = cosf(a);
+}
+
+// out[s][n] = act_out( sum_k act_in(in[s][k]) * W[n][k] + b[n] ), W in torch Linear layout (N, K).
+// fp64 accumulation: these tables are built once and feed every step.
+__global__ void linear_rows_kernel(const float *__restrict__ in, const float *__restrict__ W,
+                                   const float *__restrict__ b, float *__restrict__ out, int S, int K,
+                                   int N, int mish_in, int mish_out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * N) return;
+  const int s = idx / N, n = idx - s * N;
+  double acc = 0.0;
+  for (int k = 0; k < K; ++k) {
+    float a = in[(size_t)s * K + k];
+    if (mish_in) a = mish_precise(a);
+    acc += (double)a * (double)W[(size_t)n * K + k];
+  }
+  float v = (float)(acc + (double)b[n]);
+  if (mish_out) v = mish_precise(v);
+  out[idx] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Weight re-packers (run once per load_state_dict).
+// ------------------------------------------------------------------------------------------
+// torch Conv1d weight (Cout, Cin, k) or ConvTranspose1d weight (Cin, Cout, k)  ->  Wp[t][c][n] fp32,
+// taking kernel index ksel[t] for packed tap t.
+struct TapSel { int k[kMaxTaps]; };
+
+__global__ void pack_w_f32_kernel(const float *__restrict__ w, float *__restrict__ out, int Cout, int Cin,
+                                  int ksize, int taps, TapSel sel, int transposed) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= taps * Cin * Cout) return;
+  const int n = idx % Cout, c = (idx / Cout) % Cin, t = idx / (Cout * Cin);
+  const int kk = sel.k[t];
+  out[idx] = transposed ? w[((size_t)c * Cout + n) * ksize + kk] : w[((size_t)n * Cin + c) * ksize + kk];
+}
+
+// Same source layouts -> bf16 K-major rows: Wb[n][t * Cin_pad + c], zero padded to (Cout_pad, Cin_pad).
+__global__ void pack_w_bf16_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ out, int Cout,
+                                   int Cin, int Cout_pad, int Cin_pad, int ksize, int taps, TapSel sel,
+                                   int transposed) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)Cout_pad * taps * Cin_pad;
+  if (idx >= total) return;
+  const int c = (int)(idx % Cin_pad);
+  const int t = (int)((idx / Cin_pad) % taps);
+  const int n = (int)(idx / ((size_t)Cin_pad * taps));
+  float v = 0.f;
+  if (n < Cout && c < Cin) {
+    const int kk = sel.k[t];
+    v = transposed ? w[((size_t)c * Cout + n) * ksize + kk] : w[((size_t)n * Cin + c) * ksize + kk];
+  }
+  out[idx] = __float2bfloat16_rn(v);
+}
+
+// x fp32 (B, H, T) -> bf16 (B, H, Cpad), zero padded channels: first-layer operand of the bf16 path.
+__global__ void pack_x_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ out, size_t rows,
+                                   int T, int Cpad) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * (size_t)Cpad) return;
+  const size_t r = idx / Cpad;
+  const int c = (int)(idx - r * Cpad);
+  out[idx] = __float2bfloat16_rn(c < T ? x[r * T + c] : 0.f);
+}
+
+}  // namespace dad

@@ -1,0 +1,180 @@
+"""GaussianDiffusion with the reference's constructor, buffers and sampling entry points
+(m_diffuser/models/diffusion.py), whose reverse process runs in the native library:
+p_sample_loop = CUDA-graph replays of (U-Net + fused step kernel).  Training (`loss`, `q_sample`'s
+use in it) is out of scope for this package and raises.
+"""
+import math
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _native as N
+
+
+def cosine_beta_schedule(timesteps: int, s: float = 0.008) -> torch.Tensor:
+    """Nichol & Dhariwal cosine schedule, evaluated in fp32 exactly like diffusion.py:32-41."""
+    grid = torch.linspace(0, timesteps, timesteps + 1)
+    abar = torch.cos(((grid / timesteps) + s) / (1 + s) * torch.pi * 0.5) ** 2
+    abar = abar / abar[0]
+    return torch.clip(1 - (abar[1:] / abar[:-1]), 0.0001, 0.9999)
+
+
+def linear_beta_schedule(timesteps: int, beta_start: float = 1e-4, beta_end: float = 0.02) -> torch.Tensor:
+    """Ho et al. linear schedule (diffusion.py:44-48)."""
+    return torch.linspace(beta_start, beta_end, timesteps)
+
+
+def extract(a: torch.Tensor, t: torch.Tensor, x_shape: tuple) -> torch.Tensor:
+    """Gather a[t] and shape it (B, 1, ..., 1) for broadcasting (diffusion.py:15-29)."""
+    return a.gather(-1, t).reshape(t.shape[0], *((1,) * (len(x_shape) - 1)))
+
+
+def _derived_buffers(betas):
+    one = 1.0
+    alphas = one - betas
+    abar = torch.cumprod(alphas, dim=0)
+    abar_prev = torch.cat([torch.ones(1), abar[:-1]])
+    post_var = betas * (one - abar_prev) / (one - abar)
+    return [
+        ("betas", betas), ("alphas", alphas), ("alphas_cumprod", abar), ("alphas_cumprod_prev", abar_prev),
+        ("sqrt_alphas_cumprod", torch.sqrt(abar)),
+        ("sqrt_one_minus_alphas_cumprod", torch.sqrt(one - abar)),
+        ("sqrt_recip_alphas_cumprod", torch.sqrt(one / abar)),
+        ("sqrt_recipm1_alphas_cumprod", torch.sqrt(one / abar - 1)),
+        ("posterior_variance", post_var),
+        ("posterior_log_variance_clipped", torch.log(torch.clamp(post_var, min=1e-20))),
+        ("posterior_mean_coef1", betas * torch.sqrt(abar_prev) / (one - abar)),
+        ("posterior_mean_coef2", (one - abar_prev) * torch.sqrt(alphas) / (one - abar)),
+    ]
+
+
+class GaussianDiffusion(nn.Module):
+    """Drop-in for m_diffuser.models.diffusion.GaussianDiffusion (diffusion.py:62-71)."""
+
+    def __init__(self, model, horizon: int, observation_dim: int, action_dim: int, n_timesteps: int = 1000,
+                 loss_type: str = "l2", clip_denoised: bool = True, predict_epsilon: bool = True,
+                 beta_schedule: str = "cosine"):
+        super().__init__()
+        self.model = model
+        self.horizon = horizon
+        self.observation_dim = observation_dim
+        self.action_dim = action_dim
+        self.transition_dim = observation_dim + action_dim
+        self.n_timesteps = n_timesteps          # mutable: scripts/evaluate.py:351-353 truncates the loop with it
+        self.clip_denoised = clip_denoised
+        self.predict_epsilon = predict_epsilon
+        self.beta_schedule = beta_schedule
+        if beta_schedule == "linear":
+            betas = linear_beta_schedule(n_timesteps)
+        elif beta_schedule == "cosine":
+            betas = cosine_beta_schedule(n_timesteps)
+        else:
+            raise ValueError(f"Unknown beta schedule: {beta_schedule}")
+        for name, buf in _derived_buffers(betas):
+            self.register_buffer(name, buf)
+        if loss_type not in ("l1", "l2"):
+            raise ValueError(f"Unknown loss type: {loss_type}")
+        self.loss_type = loss_type
+
+    # ---- native plumbing ------------------------------------------------------------------------
+    def _schedule_version(self):
+        return sum(getattr(self, n)._version for n in
+                   ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
+                    "posterior_mean_coef2", "posterior_log_variance_clipped"))
+
+    def engine(self, horizon=None, device=None):
+        """Native handle with this process's weights and schedule tables loaded (rebuilt lazily on change)."""
+        device = device if device is not None else self.betas.device
+        self.model._diffusion_cfg = dict(predict_epsilon=bool(self.predict_epsilon), clip_denoised=bool(self.clip_denoised))
+        eng, ent = self.model.engine(horizon or self.horizon, device, n_timesteps=self.betas.shape[0])
+        tag = (id(self), self._schedule_version())
+        if ent.get("schedule_owner") != tag:
+            eng.set_schedule(self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod,
+                             self.posterior_mean_coef1, self.posterior_mean_coef2, self.posterior_log_variance_clipped)
+            ent["schedule_owner"] = tag
+        return eng
+
+    def _check_steps(self):
+        if self.n_timesteps > self.betas.shape[0]:
+            # the reference crashes here too (gather out of bounds in extract), SURVEY.md 3.1
+            raise IndexError("n_timesteps=%d exceeds the %d schedule entries this model was built with"
+                             % (self.n_timesteps, self.betas.shape[0]))
+
+    # ---- small tensor utilities kept for API compatibility (elementwise, not on the sampling path) ----
+    def q_sample(self, x_start, t, noise=None):
+        noise = torch.randn_like(x_start) if noise is None else noise
+        return (extract(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start
+                + extract(self.sqrt_one_minus_alphas_cumprod, t, x_start.shape) * noise)
+
+    def predict_start_from_noise(self, x_t, t, noise):
+        return (extract(self.sqrt_recip_alphas_cumprod, t, x_t.shape) * x_t
+                - extract(self.sqrt_recipm1_alphas_cumprod, t, x_t.shape) * noise)
+
+    def q_posterior(self, x_start, x_t, t) -> Tuple[torch.Tensor, torch.Tensor]:
+        mean = (extract(self.posterior_mean_coef1, t, x_t.shape) * x_start
+                + extract(self.posterior_mean_coef2, t, x_t.shape) * x_t)
+        return mean, extract(self.posterior_log_variance_clipped, t, x_t.shape)
+
+    def p_mean_variance(self, x, t) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(model_mean, posterior_log_variance (B,1,1)) as diffusion.py:182-203; the model call is native."""
+        out = self.model(x, t)
+        x_recon = self.predict_start_from_noise(x, t, out) if self.predict_epsilon else out
+        if self.clip_denoised:
+            x_recon = torch.clamp(x_recon, -1.0, 1.0)
+        return self.q_posterior(x_recon, x, t)
+
+    # ---- sampling -------------------------------------------------------------------------------
+    @torch.no_grad()
+    def p_sample(self, x, t):
+        """x_{t-1} ~ p(.|x_t) (diffusion.py:205-223): native U-Net + fused step kernel; noise = torch.randn_like."""
+        step = int(t.reshape(-1)[0])
+        eng = self.engine(x.shape[1], x.device)
+        xc = x.contiguous().float()
+        if not bool((t == step).all()):
+            raise NotImplementedError("p_sample with per-row timesteps: the fused step kernel takes one step index")
+        eps = eng.unet_forward(xc, step=step)
+        noise = torch.randn_like(x)
+        out = xc.clone()
+        return eng.step(out, eps, step, noise=noise.contiguous())
+
+    @torch.no_grad()
+    def p_sample_loop(self, shape: tuple, verbose: bool = False, noise: Optional[torch.Tensor] = None,
+                      rng: str = "philox", seed: Optional[int] = None, return_trace: bool = False):
+        """Full reverse process (diffusion.py:225-251).
+
+        x_S is drawn with torch.randn exactly where the reference draws it.  Per-step noise:
+          noise=<(n_timesteps,B,H,T) tensor>  injected (noise[k] drives step i = n_timesteps-1-k)
+          rng='torch'   torch.randn_like per step, in the reference's call order (reproduces its stream)
+          rng='philox'  drawn inside the fused step kernel (default; no HBM traffic for noise)
+        `verbose` is accepted for compatibility; the loop runs on the device without a progress bar.
+        """
+        self._check_steps()
+        device = self.betas.device
+        x = torch.randn(shape, device=device)
+        return _run_loop(self, x, noise, rng, seed, flags=0, return_trace=return_trace)
+
+    def loss(self, *a, **k):
+        raise NotImplementedError("training is outside the scope of dynamics_aware_diffusion_b200 "
+                                  "(sampling path only); train with the reference and load the state_dict here")
+
+    def forward(self, x, *args, **kwargs):
+        return self.loss(x, *args, **kwargs)
+
+
+def _run_loop(diffusion, x, noise, rng, seed, flags, return_trace=False, sample_offset=0):
+    """Shared driver of p_sample_loop / sample_loop: one dad_sample call."""
+    S = diffusion.n_timesteps
+    x = x.contiguous().float()
+    eng = diffusion.engine(x.shape[1], x.device)
+    if noise is None and rng == "torch":
+        noise = torch.stack([torch.randn_like(x) for _ in range(S)])
+    elif noise is None and rng != "philox":
+        raise ValueError("rng must be 'philox' or 'torch'")
+    if noise is not None:
+        noise = noise.to(x.device, torch.float32).contiguous()
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if noise is None else 0
+    trace = torch.empty((S,) + tuple(x.shape), device=x.device) if return_trace else None
+    eng.sample(x, S, noise_seq=noise, flags=flags, seed=seed, sample_offset=sample_offset, trace=trace)
+    return (x, trace) if return_trace else x

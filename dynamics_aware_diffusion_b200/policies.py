@@ -1,0 +1,262 @@
+"""Sampling policies with the reference's classes and signatures (m_diffuser/guides/policies.py), running
+the reverse process in the native library.
+
+  GuidedPolicy         conditioning (inpainting) + optional guidance      policies.py:13-223
+  MPCPolicy            GuidedPolicy + action_horizon                      policies.py:226-240
+  ValueGuidedPolicy    guide_fn from a value nn.Module                    policies.py:243-271
+  DynamicsAwarePolicy  per-step projection onto the dynamics-feasible set policies.py:274-485
+
+Without a guide function the whole loop is one `dad_sample` call (CUDA-graph replays).  With one, the
+gradient of the user's PyTorch module is taken by autograd each step (as the reference does) and fed to
+the fused step kernel.
+
+DynamicsAwarePolicy.sample_loop applies the projection every step (README.md:24-25, 271-275:
+x_{i-1} = project(denoise(x_i))).  In the reference `apply_projection` exists but is never called
+(SURVEY.md F3); set `policy.project_in_loop = False` to reproduce that behaviour bit-for-bit in spirit.
+"""
+from typing import Callable, Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _native as N
+from .diffusion import _run_loop
+from .projection import fold_projection, projection_alphas
+
+
+class GuidedPolicy(nn.Module):
+    def __init__(self, diffusion_model, normalizer, guide_fn: Optional[Callable] = None, guide_weight: float = 1.0,
+                 action_horizon: Optional[int] = None):
+        super().__init__()
+        self.diffusion = diffusion_model
+        self.normalizer = normalizer
+        self.guide_fn = guide_fn
+        self.guide_weight = guide_weight
+        self.horizon = diffusion_model.horizon
+        self.observation_dim = diffusion_model.observation_dim
+        self.action_dim = diffusion_model.action_dim
+        self.transition_dim = diffusion_model.transition_dim
+        self.action_horizon = action_horizon if action_horizon is not None else 1
+        self.action_buffer = []
+
+    # ---- hooks overridden by DynamicsAwarePolicy --------------------------------------------------
+    def _loop_flags(self, engine):
+        return 0
+
+    def _engine(self, device=None):
+        return self.diffusion.engine(self.horizon, device)
+
+    # ---- reference API ----------------------------------------------------------------------------
+    def apply_conditions(self, x: torch.Tensor, conditions: Dict[int, torch.Tensor]) -> torch.Tensor:
+        """x[:, h] = value for every (h, value); writes the whole transition, in place (policies.py:48-63)."""
+        for h, val in conditions.items():
+            x[:, h] = val
+        return x
+
+    def _guidance_grad(self, x, t):
+        if self.guide_fn is None or not self.guide_weight > 0:
+            return None
+        x_req = x.detach().requires_grad_(True)
+        with torch.enable_grad():
+            score = self.guide_fn(x_req, t)
+            (grad,) = torch.autograd.grad(score.sum(), x_req)
+        return grad.contiguous()
+
+    @torch.no_grad()
+    def p_sample_with_guidance(self, x, t, conditions=None):
+        """One guided, conditioned reverse step (policies.py:65-112)."""
+        step = int(t.reshape(-1)[0])
+        eng = self._engine(x.device)
+        xc = x.contiguous().float()
+        eps = eng.unet_forward(xc, step=step)
+        grad = self._guidance_grad(xc, t)
+        noise = torch.randn_like(xc)
+        flags = 0
+        if conditions:
+            eng.set_conditions(conditions, xc.shape[0])
+            flags |= N.FLAG_CONDITIONS
+        out = xc.clone()
+        return eng.step(out, eps, step, noise=noise, grad=grad, guide_w=float(self.guide_weight), flags=flags)
+
+    @torch.no_grad()
+    def sample_loop(self, batch_size: int = 1, conditions=None, verbose: bool = False,
+                    noise: Optional[torch.Tensor] = None, rng: str = "philox", seed: Optional[int] = None,
+                    return_trace: bool = False, sample_offset: int = 0):
+        """Full conditioned sampling loop (policies.py:114-149); extra keyword arguments as in
+        GaussianDiffusion.p_sample_loop."""
+        self.diffusion._check_steps()
+        device = self.diffusion.betas.device
+        x = torch.randn((batch_size, self.horizon, self.transition_dim), device=device)
+        eng = self._engine(device)
+        flags = self._loop_flags(eng)
+        if conditions:
+            eng.set_conditions(conditions, batch_size)
+            flags |= N.FLAG_CONDITIONS
+        guided = self.guide_fn is not None and self.guide_weight > 0
+        if not guided:
+            return _run_loop(self.diffusion, x, noise, rng, seed, flags, return_trace, sample_offset)
+        # guided: autograd supplies the gradient each step, the rest stays native
+        S = self.diffusion.n_timesteps
+        if conditions:
+            x = self.apply_conditions(x, {h: torch.as_tensor(v, device=device) for h, v in conditions.items()})
+        x = x.contiguous()
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        trace = []
+        for k, i in enumerate(reversed(range(S))):
+            t = torch.full((batch_size,), i, device=device, dtype=torch.long)
+            eps = eng.unet_forward(x, step=i)
+            grad = self._guidance_grad(x, t)
+            if noise is not None:
+                z = noise[k].to(device, torch.float32).contiguous()
+            elif rng == "torch":
+                z = torch.randn_like(x)
+            else:
+                z = None
+            eng.step(x, eps, i, noise=z, grad=grad, guide_w=float(self.guide_weight), flags=flags, seed=seed,
+                     sample_offset=sample_offset)
+            if return_trace:
+                trace.append(x.clone())
+        return (x, torch.stack(trace)) if return_trace else x
+
+    # ---- environment-facing glue (host side) ----------------------------------------------------------
+    def _process_observation(self, observation):
+        """dict / sequence observation -> (1, obs_dim) ndarray (policies.py:151-179)."""
+        if isinstance(observation, dict):
+            keys = observation.keys()
+            if "observation" in keys and "desired_goal" in keys:
+                state, goal = observation["observation"], observation["desired_goal"]
+                wants = self.normalizer.obs_mean.shape[0]
+                observation = np.concatenate([state, goal]) if wants == len(state) + len(goal) else state
+            elif "observation" in keys:
+                observation = observation["observation"]
+            elif "achieved_goal" in keys:
+                observation = observation["achieved_goal"]
+            else:
+                observation = np.concatenate([np.asarray(v).flatten() for v in observation.values()])
+        return np.asarray(observation).reshape(1, -1)
+
+    def _fill_action_buffer(self, trajectory):
+        """First action_horizon+1 actions of plan 0, unnormalised (policies.py:181-191)."""
+        plan = trajectory[0].detach().cpu().numpy()
+        lo, hi = self.observation_dim, self.observation_dim + self.action_dim
+        for h in range(min(self.action_horizon + 1, self.horizon)):
+            act = self.normalizer.unnormalize_actions(plan[h, lo:hi].reshape(1, -1))
+            self.action_buffer.append(np.asarray(act).flatten())
+
+    def get_action(self, observation, **kwargs) -> np.ndarray:
+        """Pop a buffered action, replanning when the buffer is empty (policies.py:193-223)."""
+        if self.action_buffer:
+            return self.action_buffer.pop(0)
+        device = self.diffusion.betas.device
+        obs = self.normalizer.normalize_observations(self._process_observation(observation))
+        start = torch.zeros(1, self.transition_dim, device=device)
+        start[:, :self.observation_dim] = torch.as_tensor(np.asarray(obs), dtype=torch.float32, device=device)
+        plan = self.sample_loop(batch_size=1, conditions={0: start}, verbose=False)
+        self._fill_action_buffer(plan)
+        return self.action_buffer.pop(0)
+
+
+class MPCPolicy(GuidedPolicy):
+    """Plan once, execute `action_horizon` actions, replan."""
+
+    def __init__(self, diffusion_model, normalizer, action_horizon: int = 8):
+        super().__init__(diffusion_model, normalizer, action_horizon=action_horizon)
+
+
+class ValueGuidedPolicy(GuidedPolicy):
+    """Guidance from a value network over the observation part of the plan."""
+
+    def __init__(self, diffusion_model, normalizer, value_model: nn.Module, guide_weight: float = 1.0,
+                 action_horizon: Optional[int] = None):
+        obs_dim = diffusion_model.observation_dim
+
+        def guide_fn(x, t):
+            return value_model(x[:, :, :obs_dim]).sum(dim=1)
+
+        super().__init__(diffusion_model, normalizer, guide_fn, guide_weight, action_horizon)
+        self.value_model = value_model
+
+
+class DynamicsAwarePolicy(GuidedPolicy):
+    """Sampling with a per-step affine projection onto trajectories consistent with x+ = A x + B u."""
+
+    def __init__(self, diffusion_model, projection_matrix: Optional[torch.Tensor] = None, normalizer=None,
+                 state_dim: int = 4, observation_dim: int = 4, action_dim: int = 2, horizon: int = 16,
+                 projection_schedule: str = "constant", projection_strength: float = 1.0,
+                 action_horizon: Optional[int] = None):
+        super().__init__(diffusion_model=diffusion_model, normalizer=normalizer, guide_fn=None, guide_weight=0.0,
+                         action_horizon=horizon if action_horizon is None else action_horizon)
+        self.projection_matrix = projection_matrix
+        self.state_dim, self.observation_dim, self.action_dim = state_dim, observation_dim, action_dim
+        self.horizon = horizon
+        self.projection_schedule = projection_schedule
+        self.projection_strength = projection_strength
+        self.n_timesteps = diffusion_model.n_timesteps
+        self.device = next(diffusion_model.parameters()).device
+        self.project_in_loop = True
+        self.project_after_inpaint = False
+        stats = ("obs_mean", "obs_std", "action_mean", "action_std")
+        for name in stats:
+            val = None
+            if normalizer is not None:
+                val = torch.from_numpy(np.asarray(getattr(normalizer, name))).float().to(self.device)
+            setattr(self, name, val)
+        self._fold = None          # (Nmat, q) fp64
+        self._loaded_on = None     # (engine id, alpha signature) the projector was last pushed to
+
+    def _get_projection_alpha(self, t: int) -> float:
+        betas = self.diffusion.betas if self.projection_schedule == "noise_schedule" else None
+        n_table = self.diffusion.betas.shape[0]
+        return float(projection_alphas(n_table, self.n_timesteps, self.projection_schedule,
+                                       self.projection_strength, betas)[t])
+
+    def unnormalize_states(self, s):
+        return s if self.obs_mean is None else s * self.obs_std + self.obs_mean
+
+    def unnormalize_actions(self, a):
+        return a if self.action_mean is None else a * self.action_std + self.action_mean
+
+    def normalize_states(self, s):
+        return s if self.obs_mean is None else (s - self.obs_mean) / self.obs_std
+
+    def normalize_actions(self, a):
+        return a if self.action_mean is None else (a - self.action_mean) / self.action_std
+
+    def _active(self):
+        return self.projection_matrix is not None and self.normalizer is not None
+
+    def _push_projector(self, eng):
+        if self._fold is None:
+            if self.observation_dim != self.state_dim:
+                raise RuntimeError("projection needs observation_dim == state_dim (the reference's apply_projection "
+                                   "fails otherwise, SURVEY.md F4)")
+            self._fold = fold_projection(self.projection_matrix.detach().cpu().numpy(), self.normalizer.obs_mean,
+                                         self.normalizer.obs_std, self.normalizer.action_mean,
+                                         self.normalizer.action_std, self.state_dim, self.action_dim, self.horizon)
+        n_table = self.diffusion.betas.shape[0]
+        betas = self.diffusion.betas if self.projection_schedule == "noise_schedule" else None
+        alphas = projection_alphas(n_table, self.n_timesteps, self.projection_schedule, self.projection_strength, betas)
+        sig = (id(eng), self.projection_schedule, float(self.projection_strength), int(self.n_timesteps), n_table)
+        if self._loaded_on != sig:
+            eng.set_projector(self._fold[0], self._fold[1], alphas)
+            self._loaded_on = sig
+
+    def _loop_flags(self, eng):
+        if not (self._active() and self.project_in_loop):
+            return 0
+        self._push_projector(eng)
+        return N.FLAG_PROJECT | (N.FLAG_PROJECT_AFTER_INPAINT if self.project_after_inpaint else 0)
+
+    @torch.no_grad()
+    def apply_projection(self, x: torch.Tensor, t: int) -> torch.Tensor:
+        """x + alpha_t (N x + q): the reference's unnormalise/concat/@P/blend/split/renormalise chain
+        (policies.py:409-485) as one native GEMM.  Returns a new tensor."""
+        if not self._active():
+            return x
+        if self._get_projection_alpha(int(t)) <= 0:
+            return x
+        eng = self._engine(x.device)
+        self._push_projector(eng)
+        return eng.project(x.contiguous().float().clone(), int(t))

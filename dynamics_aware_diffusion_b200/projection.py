@@ -1,0 +1,123 @@
+"""Host-side (numpy, fp64) construction of the dynamics projector and its fold into one affine map.
+
+  ProjectionMatrixBuilder   P = F pinv(F)            reference: m_diffuser/dynamics/projection.py:11-133
+  fit_linear_dynamics       lstsq([X U], X+)          reference: m_diffuser/dynamics/data_driven.py:75-134
+  fold_projection           DynamicsAwarePolicy.apply_projection (guides/policies.py:409-485) as
+                            y = x + alpha * (N x + q) on the flattened normalised trajectory
+  projection_alphas         _get_projection_alpha for every step (guides/policies.py:358-383)
+"""
+import numpy as np
+import torch
+
+
+class ProjectionMatrixBuilder:
+    """Builds F (trajectory = F [x0, u0..u_{T-1}]) and the orthogonal projector onto its range.
+    Concatenated layout [x0, x1, ..., xT, u0, ..., u_{T-1}] as in the reference."""
+
+    def __init__(self, A, B, state_dim: int, action_dim: int, verbose: bool = False):
+        A = np.asarray(A, dtype=np.float64)
+        B = np.asarray(B, dtype=np.float64)
+        assert A.shape == (state_dim, state_dim), f"A shape mismatch: {A.shape}"
+        assert B.shape == (state_dim, action_dim), f"B shape mismatch: {B.shape}"
+        self.A, self.B, self.state_dim, self.action_dim = A, B, state_dim, action_dim
+        self.verbose = verbose
+
+    def _build_F_matrix(self, horizon: int) -> np.ndarray:
+        n, m, T = self.state_dim, self.action_dim, horizon
+        F = np.zeros(((T + 1) * n + T * m, n + T * m))
+        # row block t of the state part is [A^t | A^{t-1}B ... AB B 0 ...]: build it by the recursion
+        # row_{t+1} = A row_t, then drop B into the column block of u_t.
+        row = np.zeros((n, n + T * m))
+        row[:, :n] = np.eye(n)
+        F[:n] = row
+        for t in range(T):
+            row = self.A @ row
+            row[:, n + t * m:n + (t + 1) * m] = self.B
+            F[(t + 1) * n:(t + 2) * n] = row
+        F[(T + 1) * n:, n:] = np.eye(T * m)
+        return F
+
+    def get_projection_matrix(self, horizon: int) -> torch.Tensor:
+        F = self._build_F_matrix(horizon)
+        P = F @ np.linalg.pinv(F)
+        if self.verbose:
+            print("projection: F %s, ||P^2-P||_F = %.2e" % (F.shape, np.linalg.norm(P @ P - P)))
+        return torch.from_numpy(P).float()
+
+    def verify_projection(self, P: torch.Tensor) -> bool:
+        return bool(torch.allclose(P @ P, P, atol=1e-4))
+
+
+def fit_linear_dynamics(states, actions, next_states, state_dim=None, verbose=False):
+    """Least-squares (A, B) with x+ ~ A x + B u."""
+    states, actions, next_states = (np.asarray(a, dtype=np.float64) for a in (states, actions, next_states))
+    if state_dim is not None and states.shape[1] > state_dim:
+        states, next_states = states[:, :state_dim], next_states[:, :state_dim]
+    n = states.shape[1]
+    theta, *_ = np.linalg.lstsq(np.hstack([states, actions]), next_states, rcond=None)
+    if verbose:
+        resid = next_states - np.hstack([states, actions]) @ theta
+        print("fit_linear_dynamics: R^2 = %.4f" % (1 - (resid ** 2).sum() / ((next_states - next_states.mean(0)) ** 2).sum()))
+    return theta[:n].T.copy(), theta[n:].T.copy()
+
+
+def fold_projection(P, obs_mean, obs_std, action_mean, action_std, state_dim, action_dim, horizon):
+    """(Nmat, q) in fp64 such that apply_projection(x, alpha) == x + alpha * (Nmat @ x + q) for the
+    row-major flattening x[h*T + j] of a normalised (H, T) trajectory, T = state_dim + action_dim.
+
+    The reference computes, per sample (policies.py:431-485):
+        c = U(x)            unnormalise, append x_H := x_{H-1}, concatenate      (affine: c = S x + s0)
+        c <- alpha (c P) + (1 - alpha) c
+        y = R(c)            drop the appended state, renormalise                 (affine: y = R c - r0, R S = I)
+    so y = x + alpha (R P^T S - I) x + alpha R (P^T s0 - s0).
+    """
+    n, m, H = state_dim, action_dim, horizon
+    T = n + m
+    P = np.asarray(P, dtype=np.float64)
+    Dc = (H + 1) * n + H * m
+    if P.shape != (Dc, Dc):
+        raise ValueError("projection matrix is %s, expected (%d, %d) for horizon %d" % (P.shape, Dc, Dc, H))
+    om, os_ = np.asarray(obs_mean, np.float64).reshape(-1), np.asarray(obs_std, np.float64).reshape(-1)
+    am, as_ = np.asarray(action_mean, np.float64).reshape(-1), np.asarray(action_std, np.float64).reshape(-1)
+    if om.shape[0] != n or os_.shape[0] != n:
+        raise ValueError("the reference projection only runs when observation_dim == state_dim (SURVEY.md F4)")
+    S = np.zeros((Dc, H * T))
+    s0 = np.zeros(Dc)
+    R = np.zeros((H * T, Dc))
+    r_shift = np.zeros(H * T)
+    for h in range(H + 1):
+        src = min(h, H - 1)
+        for j in range(n):
+            S[h * n + j, src * T + j] = os_[j]
+            s0[h * n + j] = om[j]
+    for h in range(H):
+        for j in range(n):
+            R[h * T + j, h * n + j] = 1.0 / os_[j]
+            r_shift[h * T + j] = om[j] / os_[j]
+        for j in range(m):
+            S[(H + 1) * n + h * m + j, h * T + n + j] = as_[j]
+            s0[(H + 1) * n + h * m + j] = am[j]
+            R[h * T + n + j, (H + 1) * n + h * m + j] = 1.0 / as_[j]
+            r_shift[h * T + n + j] = am[j] / as_[j]
+    Pt = P.T
+    M = R @ Pt @ S
+    q = R @ (Pt @ s0) - r_shift
+    return M - np.eye(H * T), q
+
+
+def projection_alphas(n_table, n_timesteps, schedule, strength, betas=None):
+    """alpha_i for i in [0, n_table): policies.py:358-383 (progress = i / n_timesteps)."""
+    i = np.arange(n_table, dtype=np.float64)
+    progress = i / float(n_timesteps)
+    if schedule == "constant":
+        a = np.full(n_table, float(strength))
+    elif schedule == "linear":
+        a = strength * (1 - progress)
+    elif schedule == "quadratic":
+        a = strength * (1 - progress) ** 2
+    elif schedule == "noise_schedule":
+        b = torch.as_tensor(betas, dtype=torch.float32).cpu()
+        a = torch.sqrt(1 - b).double().numpy()[:n_table] * strength     # fp32 sqrt like the reference, then .item()
+    else:
+        raise ValueError(f"Unknown projection schedule: {schedule}")
+    return np.where(a > 0, a, 0.0)      # alpha <= 0: the reference returns x unchanged (policies.py:428-429)

@@ -1,0 +1,172 @@
+/*
+ * dad_b200.h — C ABI of the B200-native reverse-diffusion sampler.
+ *
+ * This is the drop-in boundary underneath the reference's Python classes.  The
+ * reference has no FFI of its own (it is pure PyTorch); every entry point below
+ * names the reference method whose device work it replaces (paths relative to
+ * the reference root).  Plain C: opaque handle, raw pointers, sizes, a CUDA
+ * stream passed as void*.  No torch types cross this line.
+ *
+ * Conventions
+ *   - every function returns DAD_OK (0) or a negative dad_status; nothing throws.
+ *     dad_last_error() returns a human-readable message for the last failure.
+ *   - "device pointer" = memory of the handle's CUDA device.  Setup calls
+ *     (weights, schedule, projector, conditions) accept host OR device pointers
+ *     (copied with cudaMemcpyDefault); the per-step / per-loop data pointers must
+ *     be device pointers except in dad_sample_host.
+ *   - trajectories are fp32, row-major (B, H, T) exactly like the reference's
+ *     (batch, horizon, transition_dim) tensors.
+ *   - a handle is bound to one device and is not thread-safe.  All work is
+ *     enqueued on the stream the caller passes; calls return without
+ *     synchronising unless stated.
+ *   - there is no CPU fallback: on a machine without an sm_100 device
+ *     dad_create fails with DAD_ERR_DEVICE.
+ */
+#ifndef DAD_B200_H
+#define DAD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAD_ABI_VERSION 1
+#define DAD_MAX_LEVELS 8
+
+typedef enum {
+  DAD_OK = 0,
+  DAD_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
+  DAD_ERR_DEVICE = -2,      /* no usable sm_100 device, or wrong device */
+  DAD_ERR_CUDA = -3,        /* a CUDA runtime/driver call failed */
+  DAD_ERR_STATE = -4,       /* call sequence error (e.g. sampling before weights are loaded) */
+  DAD_ERR_NOMEM = -5
+} dad_status;
+
+typedef enum {
+  DAD_PRECISION_FP32 = 0,   /* SIMT fp32 everywhere: the 1e-5 parity mode */
+  DAD_PRECISION_BF16 = 1    /* tcgen05 implicit-GEMM convs, bf16 operands, fp32 accumulate */
+} dad_precision;
+
+/* flags for dad_step / dad_sample */
+#define DAD_FLAG_CONDITIONS            1u   /* inpaint the registered conditions (policies.py:109-110) */
+#define DAD_FLAG_PROJECT               2u   /* apply the registered projector every step */
+#define DAD_FLAG_PROJECT_AFTER_INPAINT 4u   /* order: denoise -> inpaint -> project (default: project -> inpaint) */
+#define DAD_FLAG_PHILOX_INIT           8u   /* dad_sample draws x_S itself (ignores the contents of x) */
+
+typedef struct dad_handle dad_handle;
+
+/* Architecture + process configuration.
+ * Mirrors TemporalUnet.__init__ (m_diffuser/models/temporal_unet.py:135-140) and
+ * GaussianDiffusion.__init__ (m_diffuser/models/diffusion.py:62-71). */
+typedef struct {
+  int32_t abi_version;          /* DAD_ABI_VERSION */
+  int32_t device;               /* CUDA device ordinal */
+  int32_t precision;            /* dad_precision */
+  int32_t transition_dim;       /* T = observation_dim + action_dim */
+  int32_t dim;                  /* base width */
+  int32_t n_levels;             /* len(dim_mults) */
+  int32_t dim_mults[DAD_MAX_LEVELS];
+  int32_t kernel_size;          /* odd, <= 7 (reference default 5) */
+  int32_t time_dim;             /* 0 -> dim (temporal_unet.py:154) */
+  int32_t horizon;              /* H; must be divisible by 2^(n_levels-1) */
+  int32_t n_timesteps;          /* length of the schedule tables (len(betas)) */
+  int32_t predict_epsilon;      /* diffusion.py:192-197 */
+  int32_t clip_denoised;        /* diffusion.py:199-200 */
+  int32_t max_batch;            /* workspace capacity in samples; larger batches are processed in chunks */
+} dad_config;
+
+/* One fp32 tensor of the U-Net state_dict; `name` is the reference's key relative to
+ * the TemporalUnet module, e.g. "downs.0.0.blocks.0.block.0.weight"
+ * (layout: SURVEY.md 8(a10); temporal_unet.py:135-197). */
+typedef struct {
+  const char *name;
+  const float *data;            /* host or device, contiguous, torch layout */
+  int64_t numel;
+} dad_tensor;
+
+/* Lifetime. Replaces nothing in the reference (module construction). */
+int dad_create(const dad_config *cfg, dad_handle **out);
+int dad_destroy(dad_handle *h);
+/* h may be NULL: returns the message of the last failed dad_create on this thread. */
+const char *dad_last_error(const dad_handle *h);
+int dad_abi_version(void);
+
+/* nn.Module.load_state_dict for the U-Net (checkpoint layout: utils/training.py:191-224).
+ * Re-packs the weights for the selected precision and precomputes the per-step
+ * time-embedding tables (temporal_unet.py:26-32,155-160,97-100 evaluated for every
+ * step index 0..n_timesteps-1).  All tensors of the architecture must be present. */
+int dad_load_weights(dad_handle *h, const dad_tensor *tensors, int32_t n_tensors);
+
+/* The five per-step coefficient buffers GaussianDiffusion registers (diffusion.py:109-128):
+ * sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, posterior_mean_coef1,
+ * posterior_mean_coef2, posterior_log_variance_clipped; each of length n_timesteps. */
+int dad_set_schedule(dad_handle *h, const float *sqrt_recip, const float *sqrt_recipm1,
+                     const float *coef1, const float *coef2, const float *log_variance,
+                     int32_t n_timesteps);
+
+/* DynamicsAwarePolicy.apply_projection (guides/policies.py:409-485) folded into one affine map on
+ * the flattened normalised (H*T) trajectory:  y = x + alpha[i] * (Nmat x + q)  with
+ * Nmat = M_P - I (row-major D x D, D = H*T), alpha per step index (policies.py:358-383).
+ * Nmat == NULL clears the projector. */
+int dad_set_projector(dad_handle *h, const float *Nmat, const float *q, const float *alpha,
+                      int32_t D, int32_t n_timesteps);
+
+/* GuidedPolicy.apply_conditions (guides/policies.py:48-63): x[:, h_idx[c], :] = vals[c].
+ * vals is (n_cond, T) when per_batch == 0 (broadcast over the batch) or (n_cond, B, T).
+ * n_cond == 0 clears. */
+int dad_set_conditions(dad_handle *h, const int32_t *h_idx, const float *vals, int32_t n_cond,
+                       int32_t per_batch, int32_t B);
+
+/* TemporalUnet.forward (temporal_unet.py:199-241).  x, eps: device (B, H, T) fp32.
+ * t: device (B,) int64 timesteps, or NULL to use the uniform `step` for every row
+ * (what the sampler does: diffusion.py:248, policies.py:146). */
+int dad_unet_forward(dad_handle *h, const float *x, const int64_t *t, int32_t step, float *eps,
+                     int32_t B, void *stream);
+
+/* Everything in p_sample_with_guidance after the model call (policies.py:84-110 =
+ * diffusion.py:159-223 + guidance + noise + inpainting) plus the projection, as ONE fused
+ * kernel: x <- step(x, model_out).  noise: device (B,H,T) or NULL for in-kernel Philox
+ * (seed, sample_offset = global index of row 0, used as the Philox subsequence).
+ * grad: device (B,H,T) guide gradient or NULL; mean += guide_w * exp(logvar) * grad (:97). */
+int dad_step(dad_handle *h, float *x, const float *model_out, const float *noise,
+             const float *grad, float guide_w, int32_t step, uint32_t flags, uint64_t seed,
+             uint64_t sample_offset, int32_t B, void *stream);
+
+/* DynamicsAwarePolicy.apply_projection(x, t) alone (guides/policies.py:409-485), in place on the
+ * device tensor x (B,H,T):  x <- x + alpha[step] * (Nmat x + q).  No inpainting. */
+int dad_project(dad_handle *h, float *x, int32_t step, int32_t B, void *stream);
+
+/* GaussianDiffusion.p_sample_loop (diffusion.py:225-251) / GuidedPolicy.sample_loop
+ * (policies.py:114-149) without a guide function: runs steps i = n_steps-1 .. 0, each step a
+ * replay of one captured CUDA graph (U-Net + fused step kernel).
+ *   x          device (B,H,T): x_S on entry (unless DAD_FLAG_PHILOX_INIT), x_0 on return;
+ *              with DAD_FLAG_CONDITIONS the conditions are applied to x_S first (policies.py:137-138)
+ *   noise_seq  device (n_steps, B, H, T): noise_seq[k] is z for step i = n_steps-1-k; NULL -> Philox
+ *   trace      device (n_steps, B, H, T) receiving x after every step, or NULL */
+int dad_sample(dad_handle *h, float *x, const float *noise_seq, uint64_t seed,
+               uint64_t sample_offset, int32_t B, int32_t n_steps, uint32_t flags, float *trace,
+               void *stream);
+
+/* Same loop with HOST buffers: copies x_S (unless PHILOX_INIT) to the device, samples, copies
+ * x_0 back and synchronises.  This is the call a non-PyTorch host binds, and the `e2e` bench leg. */
+int dad_sample_host(dad_handle *h, float *x_host, const float *noise_seq_host, uint64_t seed,
+                    uint64_t sample_offset, int32_t B, int32_t n_steps, uint32_t flags);
+
+/* Introspection for tests / benchmarks. */
+typedef struct {
+  int64_t conv_flops_per_sample;   /* 2 * MACs of all Conv1d/ConvTranspose1d of one forward (zero-padding taps counted) */
+  int64_t launches_per_step;       /* kernels of this library launched per diffusion step */
+  int64_t workspace_bytes;
+  int32_t n_conv_layers;
+  int32_t sm_count;
+} dad_info;
+int dad_get_info(const dad_handle *h, dad_info *out);
+/* Count of kernel launches issued by this library since the handle was created (graph replays
+ * count their kernel nodes). */
+int64_t dad_launch_count(const dad_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAD_B200_H */
