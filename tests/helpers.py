@@ -1,0 +1,122 @@
+"""Shared test fixtures: the parity cases, deterministic synthetic inputs, and oracle construction.
+
+Everything here is a pure function of the case name and fixed seeds, so that
+`tests/golden/make_golden.py` (run once in the build container, against the live reference) and the
+tests (run anywhere, without the reference) see identical weights, normalisers, dynamics and noise.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+# name -> architecture / process / projector configuration.  obs_dim == state_dim everywhere.
+CASES = {
+    # smallest architecture the bf16 tensor-core path accepts (channels multiples of 64)
+    "tiny": dict(n=4, m=2, dim=64, mults=(1, 2), H=16, S=20, B=4, beta="cosine", dyn="double_integrator",
+                 proj_schedule="noise_schedule", strength=1.0, wseed=101),
+    # the real PointMaze architecture (README.md:81-83), few steps
+    "pointmaze": dict(n=4, m=2, dim=128, mults=(1, 2, 4), H=32, S=8, B=2, beta="cosine", dyn="double_integrator",
+                      proj_schedule="noise_schedule", strength=1.0, wseed=102),
+    # HalfCheetah-shaped transitions and level multipliers at reduced width; D = 736 exercises the
+    # projector-GEMM path; linear beta schedule; 'linear' projection schedule
+    "cheetah_s": dict(n=17, m=6, dim=64, mults=(1, 4, 8), H=32, S=6, B=2, beta="linear", dyn="data_driven",
+                      proj_schedule="linear", strength=0.8, wseed=103),
+    # Door-shaped transitions, four levels (bottleneck length 4); 'quadratic' projection schedule
+    "door_s": dict(n=39, m=28, dim=64, mults=(1, 2, 4, 8), H=32, S=4, B=2, beta="cosine", dyn="data_driven",
+                   proj_schedule="quadratic", strength=1.0, wseed=104),
+}
+
+
+def case_T(c):
+    return c["n"] + c["m"]
+
+
+def dynamics(c):
+    """(A, B) of the case: the reference's analytical double integrator or a fitted random system."""
+    from dynamics_aware_diffusion_b200 import synthetic
+    if c["dyn"] == "double_integrator":
+        return synthetic.double_integrator(0.1)
+    A, B, X, U, Xn = synthetic.random_linear_system(c["n"], c["m"], seed=11, n_transitions=20_000)
+    return A, B, X, U, Xn
+
+
+def normalizer(c):
+    from dynamics_aware_diffusion_b200.synthetic import SyntheticNormalizer
+    return SyntheticNormalizer(c["n"], c["m"], seed=7)
+
+
+def noise_inputs(c, seed=1234):
+    """x_S (B,H,T), z (S,B,H,T), start condition (T,), goal condition (T,) -- numpy PCG64, fp32."""
+    rng = np.random.default_rng(seed)
+    T = case_T(c)
+    x_init = rng.standard_normal((c["B"], c["H"], T)).astype(np.float32)
+    z = rng.standard_normal((c["S"], c["B"], c["H"], T)).astype(np.float32)
+    start = np.concatenate([rng.standard_normal(c["n"]), np.zeros(c["m"])]).astype(np.float32)   # policies.py:212-214
+    goal = (0.5 * rng.standard_normal(T)).astype(np.float32)
+    return x_init, z, start, goal
+
+
+def value_weights(c, seed=55):
+    """Weights of the tiny value model used for the guided-sampling cases: V(x) = sum_h tanh(obs_h . w)."""
+    rng = np.random.default_rng(seed)
+    return (0.3 * rng.standard_normal(c["n"])).astype(np.float32)
+
+
+def load_golden(name):
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    z = np.load(path, allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+def golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def make_state_dict(c):
+    """Deterministic weights for the case, as {full GaussianDiffusion key: fp32 ndarray}, built without torch
+    modules of the reference: we instantiate OUR mirror classes (same parameter names, shapes and order as
+    the reference -- checked against the golden files' key list) and fill them from a numpy PCG64 stream."""
+    import torch
+    from dynamics_aware_diffusion_b200 import TemporalUnet, GaussianDiffusion
+    from dynamics_aware_diffusion_b200.synthetic import fill_state_dict
+    T = case_T(c)
+    net = TemporalUnet(T, dim=c["dim"], dim_mults=c["mults"])
+    dif = GaussianDiffusion(net, horizon=c["H"], observation_dim=c["n"], action_dim=c["m"], n_timesteps=c["S"],
+                            beta_schedule=c["beta"])
+    fill_state_dict(dif, c["wseed"])
+    return {k: v.detach().cpu().numpy() for k, v in dif.state_dict().items()}, dif
+
+
+def build_oracle(c, sd, dtype=np.float64):
+    """(UnetOracle, DiffusionOracle, ProjectionOracle, P) for a case from its state dict."""
+    from oracle.unet import UnetOracle
+    from oracle.diffusion import DiffusionOracle, BUFFER_NAMES
+    from oracle.projection import ProjectionOracle, projection_matrix, fit_linear_dynamics
+    unet = UnetOracle(sd, prefix="model.", dtype=dtype)
+    dif = DiffusionOracle({k: sd[k] for k in BUFFER_NAMES}, unet.forward, dtype=dtype)
+    dyn = dynamics(c)
+    if len(dyn) == 2:
+        A, B = dyn
+    else:
+        A, B = fit_linear_dynamics(dyn[2], dyn[3], dyn[4])
+    P = projection_matrix(A, B, c["H"])
+    nz = normalizer(c)
+    proj = ProjectionOracle(P, nz.obs_mean, nz.obs_std, nz.action_mean, nz.action_std, c["n"], c["m"], c["H"],
+                            c["S"], c["proj_schedule"], c["strength"], betas=sd["betas"], dtype=dtype)
+    return unet, dif, proj, P
+
+
+def case_json(c):
+    return json.dumps({k: (list(v) if isinstance(v, tuple) else v) for k, v in c.items()}, sort_keys=True)

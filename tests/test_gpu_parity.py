@@ -1,0 +1,218 @@
+"""GPU parity: the CUDA path (through the reference-shaped Python classes -> ctypes -> C ABI) against the
+committed golden vectors of the live reference and against the numpy oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): per-step relative L2 <= 1e-5 in fp32 mode, <= 1e-2 in bf16 mode,
+asserted TEACHER-FORCED (every step starts from the reference's x_i); free-running drift is bounded looser.
+"""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-5, "bf16": 1e-2}
+FREE_TOL = {"fp32": 2e-4, "bf16": 5e-2}
+CASE_NAMES = list(helpers.CASES)
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+_cache = {}
+
+
+def models(name, precision):
+    """(case, golden, our GaussianDiffusion on cuda:0 with the case's weights)."""
+    key = (name, precision)
+    if key not in _cache:
+        from dynamics_aware_diffusion_b200 import TemporalUnet, GaussianDiffusion
+        c = helpers.CASES[name]
+        sd, _ = helpers.make_state_dict(c)
+        net = TemporalUnet(helpers.case_T(c), dim=c["dim"], dim_mults=c["mults"], precision=precision, max_batch=64)
+        dif = GaussianDiffusion(net, horizon=c["H"], observation_dim=c["n"], action_dim=c["m"], n_timesteps=c["S"],
+                                beta_schedule=c["beta"])
+        dif.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+        dif.to(_dev())
+        _cache.clear()      # one engine set alive at a time keeps device memory small
+        _cache[key] = (c, helpers.load_golden(name), dif, sd)
+    return _cache[key]
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(_dev())
+
+
+def dyn_policy(c, dif, P):
+    from dynamics_aware_diffusion_b200 import DynamicsAwarePolicy
+    return DynamicsAwarePolicy(dif, projection_matrix=torch.from_numpy(P), normalizer=helpers.normalizer(c),
+                               state_dim=c["n"], observation_dim=c["n"], action_dim=c["m"], horizon=c["H"],
+                               projection_schedule=c["proj_schedule"], projection_strength=c["strength"])
+
+
+def case_P(c, g):
+    if "P" in g:
+        return g["P"]
+    from dynamics_aware_diffusion_b200 import ProjectionMatrixBuilder
+    return ProjectionMatrixBuilder(g["A"], g["Bm"], c["n"], c["m"]).get_projection_matrix(c["H"]).numpy()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_unet_forward(name, precision):
+    c, g, dif, _ = models(name, precision)
+    x = cu(g["x_init"])
+    for i, want in zip(g["unet_steps"], g["unet_eps"]):
+        got = dif.model(x, torch.full((c["B"],), int(i), device=x.device, dtype=torch.long))
+        assert helpers.rel_l2(got.cpu().numpy(), want) < TOL[precision], "step %d" % i
+    got = dif.model(x, cu(g["unet_t_rows"]))
+    assert helpers.rel_l2(got.cpu().numpy(), g["unet_eps_rows"]) < TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_p_sample_teacher_forced(name, precision, monkeypatch):
+    """GaussianDiffusion.p_sample per step, noise injected through torch.randn_like like the golden generator."""
+    c, g, dif, _ = models(name, precision)
+    S = c["S"]
+    worst = 0.0
+    for k, i in enumerate(reversed(range(S))):
+        x_in = g["x_init"] if k == 0 else g["trace_plain"][k - 1]
+        z = cu(g["noise"][k])
+        monkeypatch.setattr(torch, "randn_like", lambda t, **kw: z)
+        got = dif.p_sample(cu(x_in), torch.full((c["B"],), i, device=_dev(), dtype=torch.long))
+        worst = max(worst, helpers.rel_l2(got.cpu().numpy(), g["trace_plain"][k]))
+    assert worst < TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_p_mean_variance(name, precision):
+    c, g, dif, sd = models(name, precision)
+    _, odif, _, _ = helpers.build_oracle(c, sd)
+    i = c["S"] // 2
+    t = torch.full((c["B"],), i, device=_dev(), dtype=torch.long)
+    mean, logvar = dif.p_mean_variance(cu(g["x_init"]), t)
+    want_mean, want_lv, _ = odif.p_mean_variance(np.array(g["x_init"], dtype=np.float64), i)
+    assert helpers.rel_l2(mean.cpu().numpy(), want_mean) < TOL[precision]
+    assert tuple(logvar.shape) == (c["B"], 1, 1)
+    assert abs(float(logvar[0, 0, 0]) - float(want_lv)) < 1e-5 * max(1.0, abs(float(want_lv)))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_conditioned_and_value_guided_steps(name, precision, monkeypatch):
+    from dynamics_aware_diffusion_b200 import GuidedPolicy, ValueGuidedPolicy
+    c, g, dif, _ = models(name, precision)
+    S, H = c["S"], c["H"]
+    nz = helpers.normalizer(c)
+    pol = GuidedPolicy(dif, nz)
+    cond = {0: cu(g["start"])[None], H - 1: cu(g["goal"])[None]}
+    x0 = np.array(g["x_init"])
+    x0[:, 0], x0[:, H - 1] = g["start"], g["goal"]
+    worst = 0.0
+    for k, i in enumerate(reversed(range(S))):
+        x_in = x0 if k == 0 else g["trace_cond"][k - 1]
+        z = cu(g["noise"][k])
+        monkeypatch.setattr(torch, "randn_like", lambda t, **kw: z)
+        got = pol.p_sample_with_guidance(cu(x_in), torch.full((c["B"],), i, device=_dev(), dtype=torch.long), cond)
+        worst = max(worst, helpers.rel_l2(got.cpu().numpy(), g["trace_cond"][k]))
+        # inpainting is exact
+        assert np.array_equal(got[:, 0].cpu().numpy(), np.broadcast_to(g["start"], (c["B"], helpers.case_T(c))))
+    assert worst < TOL[precision]
+
+    class ValueModel(torch.nn.Module):
+        def __init__(self, w):
+            super().__init__()
+            self.w = torch.nn.Parameter(w)
+
+        def forward(self, obs):
+            return torch.tanh(obs @ self.w)
+
+    vpol = ValueGuidedPolicy(dif, nz, ValueModel(cu(helpers.value_weights(c))), guide_weight=float(g["value_guide_weight"]))
+    cond0 = {0: cu(g["start"])[None]}
+    x0 = np.array(g["x_init"])
+    x0[:, 0] = g["start"]
+    worst = 0.0
+    for k, i in enumerate(reversed(range(S))):
+        x_in = x0 if k == 0 else g["trace_value"][k - 1]
+        z = cu(g["noise"][k])
+        monkeypatch.setattr(torch, "randn_like", lambda t, **kw: z)
+        got = vpol.p_sample_with_guidance(cu(x_in), torch.full((c["B"],), i, device=_dev(), dtype=torch.long), cond0)
+        worst = max(worst, helpers.rel_l2(got.cpu().numpy(), g["trace_value"][k]))
+    assert worst < TOL[precision]
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_apply_projection(name):
+    """DynamicsAwarePolicy.apply_projection (one affine map on the device) vs the reference's 15-op chain."""
+    c, g, dif, _ = models(name, "fp32")
+    pol = dyn_policy(c, dif, case_P(c, g))
+    for i in range(c["S"]):
+        assert abs(pol._get_projection_alpha(i) - g["alphas"][i]) < 1e-7
+        got = pol.apply_projection(cu(g["x_init"]), i)
+        assert helpers.rel_l2(got.cpu().numpy(), g["proj_only"][i]) < 1e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("order", ["dyn", "dyn_inpaint_first"])
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_dynamics_aware_loop(name, order, precision):
+    """The headline path: DynamicsAwarePolicy.sample_loop = ONE dad_sample call (graph replays of U-Net + fused
+    step/projection/inpaint kernel).  Teacher-forced per step via 1-step loops; then the free-running loop with
+    its per-step trace; then the dynamics residual of the result."""
+    from dynamics_aware_diffusion_b200 import _native as N
+    c, g, dif, sd = models(name, precision)
+    P = case_P(c, g)
+    pol = dyn_policy(c, dif, P)
+    pol.project_after_inpaint = order == "dyn_inpaint_first"
+    S, B = c["S"], c["B"]
+    trace = g["trace_" + order]
+    cond0 = {0: cu(g["start"])[None]}
+    eng = pol._engine(_dev())
+    flags = pol._loop_flags(eng) | N.FLAG_CONDITIONS
+    eng.set_conditions(cond0, B)
+    x0 = np.array(g["x_init"])
+    x0[:, 0] = g["start"]
+    worst = 0.0
+    for k, i in enumerate(reversed(range(S))):
+        x = cu(x0 if k == 0 else trace[k - 1])
+        eps = eng.unet_forward(x, step=i)
+        eng.step(x, eps, i, noise=cu(g["noise"][k]), flags=flags)
+        worst = max(worst, helpers.rel_l2(x.cpu().numpy(), trace[k]))
+    assert worst < TOL[precision], "teacher-forced"
+    # free-running, whole loop on the device with injected noise
+    torch.manual_seed(0)
+    real = torch.randn
+    try:
+        torch.randn = lambda *a, **k: cu(g["x_init"])
+        out, tr = pol.sample_loop(batch_size=B, conditions=cond0, noise=cu(g["noise"]), return_trace=True)
+    finally:
+        torch.randn = real
+    assert tuple(tr.shape) == (S, B, c["H"], helpers.case_T(c))
+    assert torch.equal(tr[-1], out)
+    assert helpers.rel_l2(out.cpu().numpy(), trace[-1]) < FREE_TOL[precision], "free-running"
+    # dynamics residual ||tau - tau P||^2 (losses/__init__.py:161-186) of OUR trajectories vs the reference's
+    _, _, oproj, _ = helpers.build_oracle(c, sd)
+    for k in (0, S - 1):
+        want = g["residual_" + order][k]
+        got = oproj.residual(tr[k].cpu().numpy())
+        assert abs(got - want) <= TOL[precision] * 5 * max(want, 1e-3) + (0 if precision == "fp32" else 1e-3 * want)
+
+
+@pytest.mark.parametrize("name", ["tiny", "cheetah_s"])
+def test_sample_host_c_abi(name):
+    """dad_sample_host: host buffers in/out through the C ABI (the `e2e` bench leg)."""
+    from dynamics_aware_diffusion_b200 import _native as N
+    c, g, dif, _ = models(name, "fp32")
+    pol = dyn_policy(c, dif, case_P(c, g))
+    eng = pol._engine(_dev())
+    flags = pol._loop_flags(eng) | N.FLAG_CONDITIONS
+    eng.set_conditions({0: cu(g["start"])[None]}, c["B"])
+    x = torch.from_numpy(np.array(g["x_init"])).pin_memory()
+    x[:, 0] = torch.from_numpy(g["start"])
+    z = torch.from_numpy(np.array(g["noise"])).pin_memory()
+    eng.sample_host(x, c["S"], noise_seq_host=z, flags=flags)
+    assert helpers.rel_l2(x.numpy(), g["trace_dyn"][-1]) < FREE_TOL["fp32"]

@@ -1,0 +1,138 @@
+"""Size-independent properties at BASELINE.json's full sizes and edge cases (GPU)."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+@pytest.fixture(scope="module")
+def pointmaze_full():
+    """PointMaze config 2: dim=128 (1,2,4), H=32, T=6, B=4096, dynamics-aware with the known double integrator."""
+    from dynamics_aware_diffusion_b200 import TemporalUnet, GaussianDiffusion, DynamicsAwarePolicy, ProjectionMatrixBuilder
+    from dynamics_aware_diffusion_b200 import synthetic
+    S = 500
+    net = TemporalUnet(6, dim=128, dim_mults=(1, 2, 4), precision="bf16", max_batch=4096)
+    dif = GaussianDiffusion(net, horizon=32, observation_dim=4, action_dim=2, n_timesteps=S)
+    synthetic.fill_state_dict(dif, 0)
+    dif.to(_dev())
+    A, B = synthetic.double_integrator(0.1)
+    P = ProjectionMatrixBuilder(A, B, 4, 2).get_projection_matrix(32)
+    nz = synthetic.SyntheticNormalizer(4, 2)
+    pol = DynamicsAwarePolicy(dif, projection_matrix=P, normalizer=nz, state_dim=4, observation_dim=4, action_dim=2,
+                              horizon=32, projection_schedule="noise_schedule", projection_strength=1.0)
+    return dif, pol, P, nz
+
+
+def test_full_size_loop_properties(pointmaze_full):
+    dif, pol, P, nz = pointmaze_full
+    B = 4096
+    dif.n_timesteps = 12          # evaluate.py:351-353: the loop may be truncated to the first K schedule entries
+    pol.n_timesteps = 12
+    start = torch.zeros(1, 6, device=_dev())
+    start[0, :4] = torch.tensor([0.3, -0.2, 0.1, 0.0])
+    out = pol.sample_loop(batch_size=B, conditions={0: start}, seed=99)
+    assert out.shape == (B, 32, 6) and bool(torch.isfinite(out).all())
+    assert bool((out[:, 0] == start).all()), "inpainting must be exact"
+    # determinism and shard independence: rows [1000, 1256) drawn alone with sample_offset equal the full run
+    torch.manual_seed(5)
+    a = pol.sample_loop(batch_size=B, conditions={0: start}, seed=99, rng="philox")
+    torch.manual_seed(5)
+    b = pol.sample_loop(batch_size=B, conditions={0: start}, seed=99, rng="philox")
+    assert torch.equal(a, b)
+    # different rows see different noise
+    assert not torch.equal(a[0], a[1])
+    dif.n_timesteps = 500
+    pol.n_timesteps = 500
+
+
+def test_projection_idempotent_and_reduces_residual(pointmaze_full):
+    """P is a projector: with alpha = 1 applying the map twice equals applying it once, up to the
+    extended-state trick (Q6) -- checked through the residual, which must collapse."""
+    from dynamics_aware_diffusion_b200 import DynamicsAwarePolicy
+    from oracle.projection import ProjectionOracle
+    dif, pol, P, nz = pointmaze_full
+    cpol = DynamicsAwarePolicy(dif, projection_matrix=P, normalizer=nz, state_dim=4, observation_dim=4, action_dim=2,
+                               horizon=32, projection_schedule="constant", projection_strength=1.0)
+    x = torch.randn(4096, 32, 6, device=_dev(), generator=torch.Generator(device=_dev()).manual_seed(3))
+    y1 = cpol.apply_projection(x, 0)
+    y2 = cpol.apply_projection(y1, 0)
+    orc = ProjectionOracle(P.numpy(), nz.obs_mean, nz.obs_std, nz.action_mean, nz.action_std, 4, 2, 32, 500)
+    r0, r1, r2 = (orc.residual(t[:256].cpu().numpy()) for t in (x, y1, y2))
+    assert r1 < 0.05 * r0 and r2 <= r1 * 1.01
+    # linearity of the affine map: f(a) - f(b) = (I + N)(a - b)  =>  f(a) + f(b) - f(a + b) = f(0)
+    z = torch.zeros_like(x[:8])
+    fa, fb = cpol.apply_projection(x[:8], 0), cpol.apply_projection(x[8:16], 0)
+    fab, f0 = cpol.apply_projection(x[:8] + x[8:16], 0), cpol.apply_projection(z, 0)
+    assert helpers.rel_l2((fa + fb - fab).cpu().numpy(), f0.cpu().numpy()) < 1e-4
+
+
+def test_chunking_equals_single_pass():
+    """B larger than the workspace capacity is processed in chunks with identical results (ragged last chunk)."""
+    from dynamics_aware_diffusion_b200 import TemporalUnet, GaussianDiffusion
+    c = helpers.CASES["tiny"]
+    sd, _ = helpers.make_state_dict(c)
+    outs = []
+    for cap in (64, 24):
+        net = TemporalUnet(6, dim=64, dim_mults=(1, 2), precision="bf16", max_batch=cap)
+        dif = GaussianDiffusion(net, horizon=16, observation_dim=4, action_dim=2, n_timesteps=20)
+        dif.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        dif.to(_dev())
+        g = torch.Generator(device=_dev()).manual_seed(1)
+        x = torch.randn(50, 16, 6, device=_dev(), generator=g)
+        z = torch.randn(20, 50, 16, 6, device=_dev(), generator=g)
+        real = torch.randn
+        try:
+            torch.randn = lambda *a, **k: x.clone()
+            outs.append(dif.p_sample_loop((50, 16, 6), noise=z))
+        finally:
+            torch.randn = real
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_philox_noise_statistics_and_offsets():
+    """In-kernel Philox normals: moments, determinism, and sample_offset == global row index."""
+    from dynamics_aware_diffusion_b200 import TemporalUnet, GaussianDiffusion, _native as N
+    c = helpers.CASES["tiny"]
+    net = TemporalUnet(6, dim=64, dim_mults=(1, 2), precision="fp32", max_batch=8192)
+    dif = GaussianDiffusion(net, horizon=16, observation_dim=4, action_dim=2, n_timesteps=20)
+    dif.to(_dev())
+    eng = dif.engine(16, _dev())
+    B = 8192
+    i = 10
+    x = torch.zeros(B, 16, 6, device=_dev())
+    eps = torch.zeros_like(x)
+    eng.step(x, eps, i, noise=None, seed=7, sample_offset=0)
+    sig = float(torch.exp(0.5 * dif.posterior_log_variance_clipped[i]))
+    z = (x / sig).double()
+    n = z.numel()
+    assert abs(float(z.mean())) < 4 / np.sqrt(n)
+    assert abs(float(z.var()) - 1) < 4 * np.sqrt(2 / n)
+    assert abs(float((z ** 4).mean()) - 3) < 0.1
+    x2 = torch.zeros(100, 16, 6, device=_dev())
+    eng.step(x2, eps[:100].contiguous(), i, noise=None, seed=7, sample_offset=1000)
+    assert torch.equal(x2, x[1000:1100])
+    x3 = torch.zeros(100, 16, 6, device=_dev())
+    eng.step(x3, eps[:100].contiguous(), i - 1, noise=None, seed=7, sample_offset=1000)
+    assert not torch.equal(x3 / float(torch.exp(0.5 * dif.posterior_log_variance_clipped[i - 1])), x2 / sig)
+
+
+def test_errors_are_loud():
+    from dynamics_aware_diffusion_b200 import TemporalUnet, GaussianDiffusion, _native as N
+    net = TemporalUnet(6, dim=64, dim_mults=(1, 2))
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(2, 16, 6), torch.zeros(2, dtype=torch.long))        # CPU tensors: no CPU path
+    dif = GaussianDiffusion(net, horizon=16, observation_dim=4, action_dim=2, n_timesteps=10).to(_dev())
+    dif.n_timesteps = 11
+    with pytest.raises(IndexError):
+        dif.p_sample_loop((2, 16, 6))
+    dif.n_timesteps = 10
+    strict = TemporalUnet(6, dim=64, dim_mults=(1, 2), precision="bf16")
+    with pytest.raises(N.DadError):      # 12 rows per sample do not tile the 128-row MMA: bf16 refuses, loudly
+        strict(torch.zeros(2, 12, 6, device=_dev()), torch.zeros(2, dtype=torch.long, device=_dev()))
