@@ -1,0 +1,352 @@
+"""Benchmark of the reverse-diffusion sampling path (BASELINE.json: plans/sec, dynamics-aware, B=4096, H=32,
+500 steps; p50 diffusion-step latency).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 3 --warmup 1     # the reference's CPU sampler (torch port) on host cores
+
+One bench "step" = one full plan batch: B trajectories taken through all S reverse-diffusion steps (U-Net +
+fused step/projection/inpaint kernel per step, CUDA-graph replays).  `value` = N*B*K / time, time measured with
+CUDA events on the launching stream between barriers, max over ranks; inputs resident in HBM.  `e2e` = the same
+through the C-ABI host-buffer call (dad_sample_host): pinned host x_S in, host x_0 out, every plan batch.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+# name -> reference configuration (SURVEY.md 8(d) "Configs -> concrete shapes")
+WORKLOADS = {
+    "pointmaze": dict(n=4, m=2, dim=128, mults=(1, 2, 4), H=32, S=500, B=4096, dyn="double_integrator",
+                      label="PointMaze UMaze dynamics-aware (known double-integrator projector)"),
+    "pointmaze_guided": dict(n=4, m=2, dim=128, mults=(1, 2, 4), H=32, S=100, B=64, dyn=None,
+                             label="PointMaze UMaze guided sampling (config 0, the reference's CPU-runnable case)"),
+    "halfcheetah": dict(n=17, m=6, dim=256, mults=(1, 4, 8), H=32, S=1000, B=1024, dyn="data_driven",
+                        label="HalfCheetah dynamics-aware, 1024 plans per GPU"),
+    "door": dict(n=39, m=28, dim=256, mults=(1, 2, 4, 8), H=32, S=1000, B=4096, dyn="data_driven",
+                 label="AdroitHand Door data-driven projector"),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._halt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                mask = get(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def finish(self):
+        self._halt.set()
+        self.join(2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def projector_inputs(w):
+    """(P fp32 torch, normalizer) for the workload, via the host-side builders (ProjectionMatrixBuilder,
+    fit_linear_dynamics) on synthetic dynamics."""
+    from dynamics_aware_diffusion_b200 import ProjectionMatrixBuilder, fit_linear_dynamics, synthetic
+    nz = synthetic.SyntheticNormalizer(w["n"], w["m"], seed=7)
+    if w["dyn"] is None:
+        return None, nz
+    if w["dyn"] == "double_integrator":
+        A, B = synthetic.double_integrator(0.1)
+    else:
+        _, _, X, U, Xn = synthetic.random_linear_system(w["n"], w["m"], seed=11, n_transitions=100_000)
+        A, B = fit_linear_dynamics(X, U, Xn)
+    return ProjectionMatrixBuilder(A, B, w["n"], w["m"]).get_projection_matrix(w["H"]), nz
+
+
+def run_reference(args, w, name):
+    """The reference's CPU sampler (its op sequence restated in torch, oracle/torch_port.py) on the host cores."""
+    import numpy as np
+    import torch
+    from oracle import torch_port
+    from dynamics_aware_diffusion_b200 import TemporalUnet, GaussianDiffusion, synthetic, projection_alphas
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    T = w["n"] + w["m"]
+    S = w["S"]
+    net = TemporalUnet(T, dim=w["dim"], dim_mults=w["mults"])
+    dif = GaussianDiffusion(net, horizon=w["H"], observation_dim=w["n"], action_dim=w["m"], n_timesteps=S)
+    synthetic.fill_state_dict(dif, 0)
+    sd = {k: v.detach() for k, v in dif.state_dict().items()}
+    P, nz = projector_inputs(w)
+    projector = None
+    if P is not None:
+        al = projection_alphas(S, S, "noise_schedule", 1.0, sd["betas"])
+        projector = dict(P=P, alphas=[float(a) for a in al], n=w["n"], m=w["m"], H=w["H"],
+                         nz=tuple(torch.from_numpy(np.asarray(a, dtype=np.float32))
+                                  for a in (nz.obs_mean, nz.obs_std, nz.action_mean, nz.action_std)))
+    Bc, dsteps = args.cpu_batch, args.cpu_diffusion_steps
+    g = torch.Generator().manual_seed(1234)
+    start = torch.zeros(T)
+    start[:w["n"]] = torch.randn(w["n"], generator=g)
+
+    def one_sample():
+        x = torch.randn(Bc, w["H"], T, generator=g)
+        return torch_port.sample_loop(sd, x, lambda k: torch.randn(Bc, w["H"], T, generator=g), {0: start}, projector,
+                                      steps=dsteps)
+
+    for _ in range(args.warmup):
+        one_sample()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_sample()
+    dt = time.perf_counter() - t0
+    per_dstep = dt / (args.steps * dsteps)
+    value = Bc / (per_dstep * S)
+    sample = "B=%d plans x %d of %d diffusion steps per bench step, extrapolated linearly to %d steps" % (Bc, dsteps, S, S)
+    line = {
+        "impl": "reference", "metric": "plans/sec", "value": value, "unit": "plans/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "description": w["label"], "B": w["B"], "H": w["H"], "T": T,
+                   "diffusion_steps": S, "policy": "dynamics-aware" if P is not None else "guided"},
+        "cpu_baseline": {"value": value, "unit": "plans/s", "cores": cores, "kind": "port", "sample": sample,
+                         "ms_per_diffusion_step_at_sample_B": per_dstep * 1e3},
+        "e2e": {"value": value, "unit": "plans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="pointmaze", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="plans per GPU (default: the workload's)")
+    ap.add_argument("--diffusion-steps", type=int, default=0, help="override S (default: the workload's)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-batch", type=int, default=256)
+    ap.add_argument("--cpu-diffusion-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers-out", default="", help="write the per-layer timing table (JSON) to this file")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.batch:
+        w["B"] = args.batch
+    if args.diffusion_steps:
+        w["S"] = args.diffusion_steps
+    if args.impl == "reference":
+        return run_reference(args, w, args.workload)
+    if args.warmup < 3:
+        print("note: fewer than 3 warm-up steps requested; the timing rules ask for >= 3", file=sys.stderr)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from dynamics_aware_diffusion_b200 import (TemporalUnet, GaussianDiffusion, GuidedPolicy, DynamicsAwarePolicy,
+                                               synthetic, _native as N)
+    from dynamics_aware_diffusion_b200.distributed import broadcast_module
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU: this implementation has no CPU path"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    T, S, B, H = w["n"] + w["m"], w["S"], w["B"], w["H"]
+
+    # ---- model: random-init weights of the configured architecture, rank 0's replicated over NCCL (C1)
+    net = TemporalUnet(T, dim=w["dim"], dim_mults=w["mults"], precision=args.precision, max_batch=B)
+    dif = GaussianDiffusion(net, horizon=H, observation_dim=w["n"], action_dim=w["m"], n_timesteps=S)
+    synthetic.fill_state_dict(dif, 0 if rank == 0 else 1000 + rank)
+    dif.to(dev)
+    broadcast_module(dif, src=0)
+    P, nz = projector_inputs(w)
+    if P is not None:
+        pol = DynamicsAwarePolicy(dif, projection_matrix=P, normalizer=nz, state_dim=w["n"], observation_dim=w["n"],
+                                  action_dim=w["m"], horizon=H, projection_schedule="noise_schedule",
+                                  projection_strength=1.0)
+    else:
+        pol = GuidedPolicy(dif, nz)
+    eng = pol._engine(dev)
+    flags = pol._loop_flags(eng) | N.FLAG_CONDITIONS
+    start = torch.zeros(1, T, device=dev)
+    start[0, :w["n"]] = torch.randn(w["n"], generator=torch.Generator().manual_seed(1234)).to(dev)
+    eng.set_conditions({0: start}, B)
+    info = eng.info()
+    x = torch.empty(B, H, T, device=dev)
+    gathered = torch.empty(world * B, H, T, device=dev) if world > 1 else None
+
+    def plan_batch(k):
+        # x_S drawn in-kernel (Philox, subsequence = global sample index), then S graph replays
+        eng.sample(x, S, flags=flags | N.FLAG_PHILOX_INIT, seed=1234 + k, sample_offset=rank * B)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, x)          # C2: final trajectory gather over NVLink
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        plan_batch(k)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        plan_batch(100 + k)
+    e1.record()
+    barrier()
+    clocks = sampler.finish()
+    launches = eng.launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * B * args.steps / (ms_total * 1e-3)
+    assert bool(torch.isfinite(x).all()), "sampler produced non-finite trajectories"
+    assert bool((x[:, 0] == start).all()), "inpainting lost"
+
+    # ---- e2e: the C-ABI host-buffer call; pinned x_S in, x_0 out, every plan batch
+    xh = torch.randn(B, H, T, generator=torch.Generator().manual_seed(7 + rank)).pin_memory()
+    xs = xh.clone().pin_memory()
+    eng.sample_host(xs, S, flags=flags, seed=99, sample_offset=rank * B)        # warm-up (allocations)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        xs.copy_(xh)
+        eng.sample_host(xs, S, flags=flags, seed=200 + k, sample_offset=rank * B)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(e2e_s.item())
+    bytes_io = B * H * T * 4
+
+    line = {
+        "metric": "plans/sec", "value": value, "unit": "plans/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "description": w["label"], "B_per_gpu": B, "H": H, "T": T,
+                   "diffusion_steps": S, "policy": "dynamics-aware" if P is not None else "guided",
+                   "unet": "dim=%d mults=%s" % (w["dim"], ",".join(map(str, w["mults"]))),
+                   "noise": "in-kernel Philox", "parallelism": "batch-sharded x%d, replicated weights" % world,
+                   "l2": "working set per diffusion step (%.0f MB of activations + weights) exceeds the 126 MB L2; no flush"
+                         % (info["workspace_bytes"] / 1e6)},
+        "e2e": {"value": e2e_value, "unit": "plans/s", "h2d_bytes_per_step": bytes_io, "d2h_bytes_per_step": bytes_io},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+
+    if rank == 0:
+        pk = peaks()
+        # ---- p50 diffusion-step latency (CUDA events between graph replays)
+        step_ms = eng.sample_profile(x, S, flags=flags | N.FLAG_PHILOX_INIT, seed=5)
+        line["p50_step_latency_ms"] = statistics.median(step_ms)
+        line["p99_step_latency_ms"] = sorted(step_ms)[int(0.99 * (len(step_ms) - 1))]
+        flops_step = info["conv_flops_per_sample"] * B
+        per_step_s = ms_total * 1e-3 / (args.steps * S)
+        line["unet_tensor_frac_of_sustained"] = flops_step / per_step_s / (pk["tf_sustained"] * 1e12)
+        # ---- per-layer timing: the dominant kernel = the (instantiation, shape) with the largest share
+        groups = {}
+        table = []
+        for lay in eng.layers():
+            t_ms = eng.time_layer(lay["index"], B, iters=20)
+            fl = lay["flops_per_sample"] * B
+            lay.update(ms=t_ms, tflops=fl / (t_ms * 1e-3) / 1e12)
+            table.append(lay)
+            key = (lay["tile_n"], lay["group_width"], lay["L_out"], lay["C_in"] * lay["taps"], lay["C_out"])
+            gk = groups.setdefault(key, {"ms": 0.0, "flops": 0, "count": 0})
+            gk["ms"] += t_ms
+            gk["flops"] += fl
+            gk["count"] += 1
+        unet_ms = sum(l["ms"] for l in table)
+        key, dom = max(groups.items(), key=lambda kv: kv[1]["ms"])
+        achieved = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
+        line["roofline"] = {
+            "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+            "frac": achieved / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"] + " sustained bf16",
+            "kernel": "conv_tc_kernel<%d,%d> L=%d K=%d N=%d x%d per step" % (key[0], key[1], key[2], key[3], key[4], dom["count"]),
+            "share_of_unet_time": dom["ms"] / unet_ms, "flops_per_launch": dom["flops"] / dom["count"],
+            "avg_launch_ms": dom["ms"] / dom["count"],
+        }
+        # ---- the fused step kernel against the HBM roofline
+        st_ms = eng.time_step_kernel(B, S // 2, flags=flags, iters=50)
+        st_bytes = 12 * H * T * B          # read x, read eps, write x (Philox noise): SURVEY.md 8(d)
+        line["roofline_step_kernel"] = {
+            "bound": "hbm", "achieved": st_bytes / (st_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+            "frac": st_bytes / (st_ms * 1e-3) / 1e9 / pk["hbm"], "traffic": None, "avg_launch_ms": st_ms,
+            "bytes_per_launch": st_bytes, "note": "working set %.1f MB is L2-resident at this B" % (st_bytes / 1e6)}
+        line["unet_ms_sum_of_layers"] = unet_ms
+        if args.layers_out:
+            os.makedirs(os.path.dirname(os.path.abspath(args.layers_out)), exist_ok=True)
+            json.dump(table, open(args.layers_out, "w"), indent=1)
+        # ---- CPU baseline: the reference's op sequence in torch on the host cores, bounded sample
+        if not args.no_cpu_baseline and world == 1:
+            import io
+            import contextlib
+            buf = io.StringIO()
+            sub = argparse.Namespace(**vars(args))
+            sub.steps, sub.warmup = 2, 1
+            with contextlib.redirect_stdout(buf):
+                run_reference(sub, w, args.workload)
+            line["cpu_baseline"] = json.loads(buf.getvalue().strip().splitlines()[-1])["cpu_baseline"]
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

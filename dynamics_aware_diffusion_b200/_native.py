@@ -14,6 +14,7 @@ EXPORTS = (
     "dad_abi_version", "dad_create", "dad_destroy", "dad_last_error", "dad_load_weights",
     "dad_set_schedule", "dad_set_projector", "dad_set_conditions", "dad_unet_forward", "dad_step",
     "dad_project", "dad_sample", "dad_sample_host", "dad_get_info", "dad_launch_count",
+    "dad_sample_profile", "dad_layer_count", "dad_layer_info", "dad_time_layer", "dad_time_step_kernel",
 )
 
 
@@ -34,6 +35,12 @@ class DadTensor(ctypes.Structure):
 class DadInfo(ctypes.Structure):
     _fields_ = [("conv_flops_per_sample", ctypes.c_int64), ("launches_per_step", ctypes.c_int64),
                 ("workspace_bytes", ctypes.c_int64), ("n_conv_layers", ctypes.c_int32), ("sm_count", ctypes.c_int32)]
+
+
+class DadLayerDesc(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 96), ("L_out", ctypes.c_int32), ("C_in", ctypes.c_int32),
+                ("C_out", ctypes.c_int32), ("taps", ctypes.c_int32), ("tile_n", ctypes.c_int32),
+                ("group_width", ctypes.c_int32), ("flops_per_sample", ctypes.c_int64)]
 
 
 class DadError(RuntimeError):
@@ -75,9 +82,11 @@ def lib():
     L.dad_get_info.argtypes = [vp, ctypes.POINTER(DadInfo)]
     L.dad_launch_count.argtypes = [vp]
     L.dad_launch_count.restype = ctypes.c_int64
-    for name in EXPORTS:
-        if getattr(L, name).restype is None:
-            pass
+    L.dad_sample_profile.argtypes = [vp, vp, u64, u64, i32, i32, u32, vp, vp]
+    L.dad_layer_count.argtypes = [vp]
+    L.dad_layer_info.argtypes = [vp, i32, ctypes.POINTER(DadLayerDesc)]
+    L.dad_time_layer.argtypes = [vp, i32, i32, i32, ctypes.POINTER(ctypes.c_float), vp]
+    L.dad_time_step_kernel.argtypes = [vp, i32, i32, u32, i32, ctypes.POINTER(ctypes.c_float), vp]
     if L.dad_abi_version() != DAD_ABI_VERSION:
         raise RuntimeError("libdad_b200.so ABI %d != binding ABI %d; rebuild" % (L.dad_abi_version(), DAD_ABI_VERSION))
     _lib = L

@@ -613,6 +613,29 @@ int check_dims(dad_handle *h, const dad_tensor *t, const std::string &name, long
 
 }  // namespace
 
+namespace {
+template <typename F>
+int time_launches(dad_handle *h, cudaStream_t st, int iters, float *ms, F &&launch) {
+  cudaEvent_t a, b;
+  CK(h, cudaEventCreate(&a));
+  CK(h, cudaEventCreate(&b));
+  int rc = launch();
+  if (rc) return rc;
+  CK(h, cudaEventRecord(a, st));
+  for (int i = 0; i < iters; ++i)
+    if ((rc = launch())) return rc;
+  CK(h, cudaEventRecord(b, st));
+  CK(h, cudaStreamSynchronize(st));
+  CK(h, cudaGetLastError());
+  float t = 0.f;
+  CK(h, cudaEventElapsedTime(&t, a, b));
+  *ms = t / (float)iters;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return DAD_OK;
+}
+}  // namespace
+
 // =================================================================================================
 extern "C" {
 
@@ -1061,5 +1084,114 @@ int dad_get_info(const dad_handle *h, dad_info *out) {
 }
 
 int64_t dad_launch_count(const dad_handle *h) { return h ? h->launches : 0; }
+
+int dad_sample_profile(dad_handle *h, float *x, uint64_t seed, uint64_t sample_offset, int32_t B, int32_t n_steps,
+                       uint32_t flags, float *step_ms, void *stream) {
+  if (!h || !x || !step_ms || B < 1) return DAD_ERR_INVALID;
+  if (!h->have_weights || !h->have_sched) DAD_FAIL(h, DAD_ERR_STATE, "dad_sample_profile before weights and schedule are set");
+  if (B > h->cfg.max_batch) DAD_FAIL(h, DAD_ERR_INVALID, "dad_sample_profile needs B <= max_batch");
+  if (n_steps < 1 || n_steps > h->cfg.n_timesteps) DAD_FAIL(h, DAD_ERR_INVALID, "n_steps outside the schedule");
+  const bool project = (flags & DAD_FLAG_PROJECT) != 0;
+  if (project && !h->projD) DAD_FAIL(h, DAD_ERR_STATE, "DAD_FLAG_PROJECT without dad_set_projector");
+  CK(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  LoopState ls{};
+  ls.step = n_steps - 1;
+  ls.n_steps = n_steps;
+  ls.flags = flags;
+  ls.x = x;
+  ls.seed = seed;
+  ls.sample_offset = sample_offset;
+  fill_cond(h, ls, 0);
+  int rc = set_loop_state(h, ls, st);
+  if (rc) return rc;
+  const bool draw = (flags & DAD_FLAG_PHILOX_INIT) != 0;
+  if (draw || ((flags & DAD_FLAG_CONDITIONS) && h->n_cond)) {
+    init_x_kernel<<<cdiv((size_t)B * h->D / 4, 256), 256, 0, st>>>(h->d_ls, h->d_cond, B, h->D, h->cfg.transition_dim, draw ? 1 : 0);
+    h->launches += 1;
+  }
+  GraphEntry *ge = nullptr;
+  if ((rc = get_graph(h, B, project, &ge))) return rc;
+  std::vector<cudaEvent_t> ev(n_steps + 1);
+  for (auto &e : ev) CK(h, cudaEventCreate(&e));
+  CK(h, cudaEventRecord(ev[0], st));
+  for (int s = 0; s < n_steps; ++s) {
+    CK(h, cudaGraphLaunch(ge->exec, st));
+    CK(h, cudaEventRecord(ev[s + 1], st));
+  }
+  h->launches += ge->kernels * n_steps;
+  CK(h, cudaStreamSynchronize(st));
+  for (int s = 0; s < n_steps; ++s) CK(h, cudaEventElapsedTime(&step_ms[s], ev[s], ev[s + 1]));
+  for (auto &e : ev) cudaEventDestroy(e);
+  return DAD_OK;
+}
+
+int dad_layer_count(const dad_handle *h) { return h ? (int)h->ops.size() : 0; }
+
+int dad_layer_info(const dad_handle *h, int32_t index, dad_layer_desc *out) {
+  if (!h || !out || index < 0 || index >= (int)h->ops.size()) return DAD_ERR_INVALID;
+  const ConvOp &op = h->ops[index];
+  memset(out, 0, sizeof(*out));
+  std::string nm = op.wname.substr(0, op.wname.size() - 7);   // strip ".weight"
+  if (op.transposed) nm += op.g.out_phase ? "[odd]" : "[even]";
+  snprintf(out->name, sizeof(out->name), "%s", nm.c_str());
+  out->L_out = op.g.L_out;
+  out->C_in = op.Cin_real;
+  out->C_out = op.g.Cout;
+  out->taps = op.g.taps;
+  out->tile_n = op.BN;
+  out->group_width = op.GW;
+  out->flops_per_sample = 2LL * op.g.L_out * op.g.taps * op.Cin_real * op.g.Cout;
+  return DAD_OK;
+}
+
+
+int dad_time_layer(dad_handle *h, int32_t index, int32_t B, int32_t iters, float *ms, void *stream) {
+  if (!h || !ms || index < 0 || index >= (int)h->ops.size() || iters < 1 || B < 1 || B > h->cfg.max_batch) return DAD_ERR_INVALID;
+  if (!h->have_weights) DAD_FAIL(h, DAD_ERR_STATE, "dad_time_layer before dad_load_weights");
+  CK(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  LoopState ls{};
+  ls.step = 0;
+  ls.n_steps = 1;
+  ls.x = h->d_xtmp;
+  int rc = set_loop_state(h, ls, st);
+  if (rc) return rc;
+  const ConvOp &op = h->ops[index];
+  h->counting = 0;
+  rc = time_launches(h, st, iters, ms, [&]() { return h->bf16 ? enqueue_tc(h, op, B, st) : enqueue_f32(h, op, B, st); });
+  h->launches += h->counting;
+  return rc;
+}
+
+int dad_time_step_kernel(dad_handle *h, int32_t B, int32_t step, uint32_t flags, int32_t iters, float *ms, void *stream) {
+  if (!h || !ms || iters < 1 || B < 1 || B > h->cfg.max_batch) return DAD_ERR_INVALID;
+  if (!h->have_sched) DAD_FAIL(h, DAD_ERR_STATE, "dad_time_step_kernel before dad_set_schedule");
+  if (step < 0 || step >= h->cfg.n_timesteps) return DAD_ERR_INVALID;
+  const bool project = (flags & DAD_FLAG_PROJECT) != 0;
+  if (project && !h->projD) DAD_FAIL(h, DAD_ERR_STATE, "DAD_FLAG_PROJECT without dad_set_projector");
+  CK(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t n = (size_t)B * h->D;
+  if (n > h->hostx_cap) {
+    int rc;
+    if ((rc = dev_alloc(h, &h->d_hostx, n))) return rc;
+    h->hostx_cap = n;
+  }
+  CK(h, cudaMemsetAsync(h->d_hostx, 0, n * sizeof(float), st));
+  LoopState ls{};
+  ls.step = step;
+  ls.n_steps = step + 1;
+  ls.flags = flags;
+  ls.x = h->d_hostx;
+  ls.seed = 1;
+  fill_cond(h, ls, 0);
+  int rc = set_loop_state(h, ls, st);
+  if (rc) return rc;
+  h->counting = 0;
+  rc = time_launches(h, st, iters, ms, [&]() { return enqueue_step(h, h->d_eps, B, project, false, st); });
+  h->launches += h->counting;
+  return rc;
+}
 
 }  // extern "C"

@@ -177,6 +177,39 @@ class Engine:
                                           int(sample_offset), x_host.shape[0], int(n_steps), int(flags)))
         return x_host
 
+    # ---- measurement hooks ----------------------------------------------------------------------
+    def sample_profile(self, x, n_steps, flags=0, seed=0, sample_offset=0):
+        """sample() with Philox noise, returning per-diffusion-step device times in ms (list of n_steps)."""
+        x = _f32c(x, "x")
+        buf = (ctypes.c_float * int(n_steps))()
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.dad_sample_profile(self.handle, _ptr(x), int(seed), int(sample_offset), x.shape[0],
+                                                 int(n_steps), int(flags), buf, _stream()))
+        return list(buf)
+
+    def layers(self):
+        out = []
+        for i in range(self.lib.dad_layer_count(self.handle)):
+            d = N.DadLayerDesc()
+            self._ck(self.lib.dad_layer_info(self.handle, i, ctypes.byref(d)))
+            out.append({"index": i, "name": d.name.decode(), "L_out": d.L_out, "C_in": d.C_in, "C_out": d.C_out,
+                        "taps": d.taps, "tile_n": d.tile_n, "group_width": d.group_width,
+                        "flops_per_sample": d.flops_per_sample})
+        return out
+
+    def time_layer(self, index, B, iters=20):
+        ms = ctypes.c_float()
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.dad_time_layer(self.handle, int(index), int(B), int(iters), ctypes.byref(ms), _stream()))
+        return ms.value
+
+    def time_step_kernel(self, B, step, flags=0, iters=20):
+        ms = ctypes.c_float()
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.dad_time_step_kernel(self.handle, int(B), int(step), int(flags), int(iters),
+                                                   ctypes.byref(ms), _stream()))
+        return ms.value
+
     def info(self):
         out = N.DadInfo()
         self._ck(self.lib.dad_get_info(self.handle, ctypes.byref(out)))

@@ -166,6 +166,31 @@ int dad_get_info(const dad_handle *h, dad_info *out);
  * count their kernel nodes). */
 int64_t dad_launch_count(const dad_handle *h);
 
+/* ---- measurement hooks (bench.py; no reference counterpart) ------------------------------------ */
+
+/* dad_sample with Philox noise that also returns the device time of every diffusion step (CUDA events
+ * recorded on `stream` between the graph replays).  step_ms: HOST array of n_steps floats, step_ms[k] is
+ * the k-th executed step (i = n_steps-1-k).  Synchronises `stream` before returning.  B <= max_batch. */
+int dad_sample_profile(dad_handle *h, float *x, uint64_t seed, uint64_t sample_offset, int32_t B,
+                       int32_t n_steps, uint32_t flags, float *step_ms, void *stream);
+
+/* One convolution layer of the U-Net plan (a Conv1d / ConvTranspose1d phase of temporal_unet.py). */
+typedef struct {
+  char name[96];            /* state_dict stem of the weight, e.g. "mid_block1.blocks.0.block.0" */
+  int32_t L_out, C_in, C_out, taps;
+  int32_t tile_n, group_width;   /* bf16 path: N-tile and GroupNorm width of the kernel instantiation (0 = no GN) */
+  int64_t flops_per_sample;      /* 2 * L_out * taps * C_in(real) * C_out */
+} dad_layer_desc;
+int dad_layer_count(const dad_handle *h);
+int dad_layer_info(const dad_handle *h, int32_t index, dad_layer_desc *out);
+/* Times `iters` back-to-back launches of layer `index` at batch B on `stream` with CUDA events (after one
+ * untimed launch); *ms_per_launch receives the average.  Operates on the handle's own workspaces (their
+ * contents are whatever the last forward left there).  Synchronises. */
+int dad_time_layer(dad_handle *h, int32_t index, int32_t B, int32_t iters, float *ms_per_launch, void *stream);
+/* Same for the fused step kernel(s) (K7 [+K8]) at step index `step`, Philox noise, on scratch trajectories. */
+int dad_time_step_kernel(dad_handle *h, int32_t B, int32_t step, uint32_t flags, int32_t iters,
+                         float *ms_per_launch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,7 +14,28 @@ pytestmark = pytest.mark.gpu
 
 TOL = {"fp32": 1e-5, "bf16": 1e-2}
 FREE_TOL = {"fp32": 2e-4, "bf16": 5e-2}
+# The ONE ill-conditioned step: with the cosine schedule beta_{S-1} is clipped to 0.9999 (diffusion.py:41), so
+# the first reverse step computes x0 = 100 x - 99.99 eps and the posterior mean has d(mean)/d(eps) = 99.98
+# (every other step: < 1.5).  Any bf16 evaluation of eps (ours: 8e-3 relative; stock torch.autocast: 1.1e-2,
+# tools/gpu_probe.py) is amplified ~40x there, and the clamp at +-1 leaves only ~0.3 % of the entries free, so
+# the step error is the luck of a handful of elements.  bf16 mode is therefore held to 1e-2 on every
+# well-conditioned step and to ILL_TOL on that one, and its eps error must not exceed stock autocast-bf16
+# PyTorch's on the same input (test_bf16_unet_no_worse_than_stock_autocast).
+ILL_TOL = 5e-2
 CASE_NAMES = list(helpers.CASES)
+
+
+def step_tols(c, sd, precision):
+    """Per-step tolerance, index k = loop iteration (step i = S-1-k)."""
+    tol = []
+    for i in reversed(range(c["S"])):
+        amp = float(sd["posterior_mean_coef1"][i] * sd["sqrt_recipm1_alphas_cumprod"][i])
+        tol.append(ILL_TOL if (precision == "bf16" and amp > 10.0) else TOL[precision])
+    return tol
+
+
+def worst_excess(errs, tols):
+    return max(e / t for e, t in zip(errs, tols))
 
 
 def _dev():
@@ -75,16 +96,32 @@ def test_unet_forward(name, precision):
 @pytest.mark.parametrize("name", CASE_NAMES)
 def test_p_sample_teacher_forced(name, precision, monkeypatch):
     """GaussianDiffusion.p_sample per step, noise injected through torch.randn_like like the golden generator."""
-    c, g, dif, _ = models(name, precision)
+    c, g, dif, sd = models(name, precision)
     S = c["S"]
-    worst = 0.0
+    errs = []
     for k, i in enumerate(reversed(range(S))):
         x_in = g["x_init"] if k == 0 else g["trace_plain"][k - 1]
         z = cu(g["noise"][k])
         monkeypatch.setattr(torch, "randn_like", lambda t, **kw: z)
         got = dif.p_sample(cu(x_in), torch.full((c["B"],), i, device=_dev(), dtype=torch.long))
-        worst = max(worst, helpers.rel_l2(got.cpu().numpy(), g["trace_plain"][k]))
-    assert worst < TOL[precision]
+        errs.append(helpers.rel_l2(got.cpu().numpy(), g["trace_plain"][k]))
+    assert worst_excess(errs, step_tols(c, sd, precision)) < 1.0, errs
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_bf16_unet_no_worse_than_stock_autocast(name):
+    """Calibration of the bf16 mode: the hand-written tcgen05 path deviates from the fp32 reference no more than
+    stock torch.autocast(bf16) running the same network (oracle/torch_port.py) on this GPU."""
+    from oracle import torch_port
+    c, g, dif, sd = models(name, "bf16")
+    x = cu(g["x_init"])
+    w = {k[len("model."):]: cu(v) for k, v in sd.items() if k.startswith("model.")}
+    for i, want in zip(g["unet_steps"], g["unet_eps"]):
+        t = torch.full((c["B"],), int(i), device=_dev(), dtype=torch.long)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            e_stock = helpers.rel_l2(torch_port.unet_forward(w, x, t).float().cpu().numpy(), want)
+        e_ours = helpers.rel_l2(dif.model(x, t).cpu().numpy(), want)
+        assert e_ours <= 1.1 * e_stock, (e_ours, e_stock)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -105,23 +142,24 @@ def test_p_mean_variance(name, precision):
 @pytest.mark.parametrize("name", CASE_NAMES)
 def test_conditioned_and_value_guided_steps(name, precision, monkeypatch):
     from dynamics_aware_diffusion_b200 import GuidedPolicy, ValueGuidedPolicy
-    c, g, dif, _ = models(name, precision)
+    c, g, dif, sd = models(name, precision)
     S, H = c["S"], c["H"]
+    tols = step_tols(c, sd, precision)
     nz = helpers.normalizer(c)
     pol = GuidedPolicy(dif, nz)
     cond = {0: cu(g["start"])[None], H - 1: cu(g["goal"])[None]}
     x0 = np.array(g["x_init"])
     x0[:, 0], x0[:, H - 1] = g["start"], g["goal"]
-    worst = 0.0
+    errs = []
     for k, i in enumerate(reversed(range(S))):
         x_in = x0 if k == 0 else g["trace_cond"][k - 1]
         z = cu(g["noise"][k])
         monkeypatch.setattr(torch, "randn_like", lambda t, **kw: z)
         got = pol.p_sample_with_guidance(cu(x_in), torch.full((c["B"],), i, device=_dev(), dtype=torch.long), cond)
-        worst = max(worst, helpers.rel_l2(got.cpu().numpy(), g["trace_cond"][k]))
+        errs.append(helpers.rel_l2(got.cpu().numpy(), g["trace_cond"][k]))
         # inpainting is exact
         assert np.array_equal(got[:, 0].cpu().numpy(), np.broadcast_to(g["start"], (c["B"], helpers.case_T(c))))
-    assert worst < TOL[precision]
+    assert worst_excess(errs, tols) < 1.0, errs
 
     class ValueModel(torch.nn.Module):
         def __init__(self, w):
@@ -135,14 +173,14 @@ def test_conditioned_and_value_guided_steps(name, precision, monkeypatch):
     cond0 = {0: cu(g["start"])[None]}
     x0 = np.array(g["x_init"])
     x0[:, 0] = g["start"]
-    worst = 0.0
+    errs = []
     for k, i in enumerate(reversed(range(S))):
         x_in = x0 if k == 0 else g["trace_value"][k - 1]
         z = cu(g["noise"][k])
         monkeypatch.setattr(torch, "randn_like", lambda t, **kw: z)
         got = vpol.p_sample_with_guidance(cu(x_in), torch.full((c["B"],), i, device=_dev(), dtype=torch.long), cond0)
-        worst = max(worst, helpers.rel_l2(got.cpu().numpy(), g["trace_value"][k]))
-    assert worst < TOL[precision]
+        errs.append(helpers.rel_l2(got.cpu().numpy(), g["trace_value"][k]))
+    assert worst_excess(errs, tols) < 1.0, errs
 
 
 @pytest.mark.parametrize("name", CASE_NAMES)
@@ -176,13 +214,13 @@ def test_dynamics_aware_loop(name, order, precision):
     eng.set_conditions(cond0, B)
     x0 = np.array(g["x_init"])
     x0[:, 0] = g["start"]
-    worst = 0.0
+    errs = []
     for k, i in enumerate(reversed(range(S))):
         x = cu(x0 if k == 0 else trace[k - 1])
         eps = eng.unet_forward(x, step=i)
         eng.step(x, eps, i, noise=cu(g["noise"][k]), flags=flags)
-        worst = max(worst, helpers.rel_l2(x.cpu().numpy(), trace[k]))
-    assert worst < TOL[precision], "teacher-forced"
+        errs.append(helpers.rel_l2(x.cpu().numpy(), trace[k]))
+    assert worst_excess(errs, step_tols(c, sd, precision)) < 1.0, ("teacher-forced", errs)
     # free-running, whole loop on the device with injected noise
     torch.manual_seed(0)
     real = torch.randn

@@ -1,0 +1,167 @@
+"""CPU tests of the host-side logic: the affine fold of apply_projection, projection schedules, the projector
+builder, state_dict round-trips, checkpoint layout, the policies' environment glue, the C ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from dynamics_aware_diffusion_b200 import (TemporalUnet, GaussianDiffusion, GuidedPolicy, MPCPolicy,
+                                           DynamicsAwarePolicy, ProjectionMatrixBuilder, fit_linear_dynamics,
+                                           fold_projection, projection_alphas, _native)
+
+CASE_NAMES = list(helpers.CASES)
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_fold_projection_equals_reference_chain(name):
+    """y = x + alpha (N x + q) reproduces the reference's apply_projection outputs (golden `proj_only`)."""
+    c = helpers.CASES[name]
+    g = helpers.load_golden(name)
+    if "P" in g:
+        P = g["P"]
+    else:
+        P = ProjectionMatrixBuilder(g["A"], g["Bm"], c["n"], c["m"]).get_projection_matrix(c["H"]).numpy()
+    nz = helpers.normalizer(c)
+    Nm, q = fold_projection(P, nz.obs_mean, nz.obs_std, nz.action_mean, nz.action_std, c["n"], c["m"], c["H"])
+    sd, _ = helpers.make_state_dict(c)
+    al = projection_alphas(c["S"], c["S"], c["proj_schedule"], c["strength"], sd["betas"])
+    np.testing.assert_allclose(al, np.where(g["alphas"] > 0, g["alphas"], 0), atol=1e-7)
+    x = g["x_init"].reshape(c["B"], -1).astype(np.float64)
+    for i in range(c["S"]):
+        y = x + al[i] * (x @ Nm.T + q)
+        assert helpers.rel_l2(y.reshape(g["x_init"].shape), g["proj_only"][i]) < 2e-5
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_projection_builder_matches_reference(name):
+    c = helpers.CASES[name]
+    g = helpers.load_golden(name)
+    b = ProjectionMatrixBuilder(g["A"], g["Bm"], c["n"], c["m"])
+    P = b.get_projection_matrix(c["H"])
+    assert P.dtype == torch.float32
+    D = (c["H"] + 1) * c["n"] + c["H"] * c["m"]
+    assert tuple(P.shape) == (D, D)
+    np.testing.assert_allclose(np.diagonal(P.numpy()), g["P_diag"], atol=2e-5)
+    np.testing.assert_allclose(P[0].numpy(), g["P_row0"], atol=2e-5)
+    assert b.verify_projection(P)
+    if "A_true" in g:
+        dyn = helpers.dynamics(c)
+        A, Bm = fit_linear_dynamics(dyn[2], dyn[3], dyn[4])
+        np.testing.assert_allclose(A, g["A"], atol=1e-9)
+        np.testing.assert_allclose(Bm, g["Bm"], atol=1e-9)
+
+
+def test_projection_schedules():
+    betas = np.linspace(1e-4, 0.02, 10).astype(np.float32)
+    assert np.allclose(projection_alphas(10, 10, "constant", 0.5), 0.5)
+    assert np.allclose(projection_alphas(10, 10, "linear", 1.0), 1 - np.arange(10) / 10)
+    assert np.allclose(projection_alphas(10, 10, "quadratic", 2.0), 2 * (1 - np.arange(10) / 10) ** 2)
+    assert np.allclose(projection_alphas(10, 10, "noise_schedule", 1.0, betas), np.sqrt(1 - betas), atol=1e-7)
+    # truncated loops (evaluate.py:351-353): progress uses the policy's n_timesteps; alpha <= 0 -> no projection
+    a = projection_alphas(10, 5, "linear", 1.0)
+    assert a[5] == 0 and np.all(a[6:] == 0) and a[0] == 1
+    with pytest.raises(ValueError):
+        projection_alphas(10, 10, "cubic", 1.0)
+
+
+def test_state_dict_roundtrip_and_checkpoint_layout(tmp_path):
+    """Keys/shapes are the reference's (golden `keys`); a training checkpoint dict (utils/training.py:193-211)
+    loads through model_state_dict."""
+    c = helpers.CASES["pointmaze"]
+    sd, dif = helpers.make_state_dict(c)
+    g = helpers.load_golden("pointmaze")
+    assert list(sd.keys()) == str(g["keys"]).split("\n")
+    assert sum(v.size for k, v in sd.items() if k.startswith("model.")) == 15_860_486
+    ckpt = {"epoch": 3, "global_step": 10, "model_state_dict": dif.state_dict(),
+            "config": {"horizon": 32, "observation_dim": 4, "action_dim": 2, "n_timesteps": c["S"], "beta_schedule": "cosine"}}
+    path = tmp_path / "checkpoint_step_10.pt"
+    torch.save(ckpt, path)
+    net = TemporalUnet(6, dim=128, dim_mults=(1, 2, 4))
+    dif2 = GaussianDiffusion(net, horizon=32, observation_dim=4, action_dim=2, n_timesteps=c["S"])
+    dif2.load_state_dict(torch.load(path, weights_only=False)["model_state_dict"], strict=True)
+    for k, v in dif2.state_dict().items():
+        assert np.array_equal(v.numpy(), sd[k])
+
+
+def test_constructor_surface_matches_reference():
+    """Argument names and defaults of the mirrored constructors."""
+    import inspect
+    sig = inspect.signature(TemporalUnet.__init__).parameters
+    assert [p for p in sig][1:6] == ["transition_dim", "dim", "dim_mults", "kernel_size", "time_dim"]
+    assert sig["dim"].default == 128 and sig["dim_mults"].default == (1, 2, 4, 8) and sig["kernel_size"].default == 5
+    sig = inspect.signature(GaussianDiffusion.__init__).parameters
+    assert [p for p in sig][1:] == ["model", "horizon", "observation_dim", "action_dim", "n_timesteps", "loss_type",
+                                   "clip_denoised", "predict_epsilon", "beta_schedule"]
+    assert sig["n_timesteps"].default == 1000 and sig["beta_schedule"].default == "cosine"
+    sig = inspect.signature(DynamicsAwarePolicy.__init__).parameters
+    assert [p for p in sig][1:] == ["diffusion_model", "projection_matrix", "normalizer", "state_dim", "observation_dim",
+                                   "action_dim", "horizon", "projection_schedule", "projection_strength", "action_horizon"]
+    sig = inspect.signature(GuidedPolicy.__init__).parameters
+    assert [p for p in sig][1:] == ["diffusion_model", "normalizer", "guide_fn", "guide_weight", "action_horizon"]
+    assert inspect.signature(MPCPolicy.__init__).parameters["action_horizon"].default == 8
+    with pytest.raises(ValueError):
+        GaussianDiffusion(TemporalUnet(6, dim=64, dim_mults=(1, 2)), 16, 4, 2, beta_schedule="sigmoid")
+
+
+def test_policy_host_glue():
+    """_process_observation / _fill_action_buffer / action buffering (policies.py:151-223), no device work."""
+    c = helpers.CASES["tiny"]
+    net = TemporalUnet(6, dim=64, dim_mults=(1, 2))
+    dif = GaussianDiffusion(net, horizon=16, observation_dim=4, action_dim=2, n_timesteps=20)
+    nz = helpers.normalizer(c)
+    pol = MPCPolicy(dif, nz, action_horizon=3)
+    o = pol._process_observation({"observation": np.arange(4.0), "desired_goal": np.ones(2), "achieved_goal": np.zeros(2)})
+    assert o.shape == (1, 4) and np.array_equal(o[0], np.arange(4.0))
+    assert pol._process_observation({"achieved_goal": np.ones(3)}).shape == (1, 3)
+    assert pol._process_observation(np.arange(4.0)).shape == (1, 4)
+    plan = torch.zeros(1, 16, 6)
+    plan[0, :, 4:] = torch.arange(32.0).reshape(16, 2)
+    pol._fill_action_buffer(plan)
+    assert len(pol.action_buffer) == 4            # range(0, action_horizon + 1)   (policies.py:188)
+    np.testing.assert_allclose(pol.action_buffer[1], nz.unnormalize_actions(np.array([[2.0, 3.0]]))[0], rtol=1e-6)
+    first = pol.get_action(np.zeros(4))           # pops the buffer: no replanning, no device needed
+    np.testing.assert_allclose(first, nz.unnormalize_actions(np.array([[0.0, 1.0]]))[0], rtol=1e-6)
+    assert len(pol.action_buffer) == 3
+
+
+def test_no_cpu_fallback():
+    net = TemporalUnet(6, dim=64, dim_mults=(1, 2))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        net(torch.zeros(2, 16, 6), torch.zeros(2, dtype=torch.long))
+    dif = GaussianDiffusion(net, horizon=16, observation_dim=4, action_dim=2, n_timesteps=20)
+    with pytest.raises(RuntimeError):
+        dif.p_sample_loop((2, 16, 6))
+    with pytest.raises(NotImplementedError):
+        dif.loss(torch.zeros(2, 16, 6))
+
+
+def test_c_abi_exports_every_declared_symbol(built_lib):
+    """The shared library loads and exports exactly what include/dad_b200.h declares (no compute calls)."""
+    hdr = open(os.path.join(helpers.ROOT, "include", "dad_b200.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|int64_t|const char \*)\s*\*?\s*(dad_[a-z_0-9]+)\s*\(", hdr, flags=re.M))
+    assert declared == set(_native.EXPORTS), declared ^ set(_native.EXPORTS)
+    lib = ctypes.CDLL(built_lib)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.dad_abi_version() == _native.DAD_ABI_VERSION
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-box behaviour")
+def test_create_fails_loudly_without_a_gpu(built_lib):
+    from dynamics_aware_diffusion_b200.engine import Engine
+    with pytest.raises(_native.DadError) as e:
+        Engine(transition_dim=6, dim=64, dim_mults=(1, 2), kernel_size=5, time_dim=None, horizon=16, n_timesteps=10,
+               precision="fp32", max_batch=4, device="cuda:0")
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(helpers.ROOT, "dynamics_aware_diffusion_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn

@@ -139,3 +139,21 @@ def test_free_running_loop_matches_when_unclamped_drift_is_small(setup):
     c, sd, g, unet, dif, proj, P = setup
     x = dif.sample_loop(g["x_init"], g["noise"], conditions={0: g["start"]}, projector=proj)
     assert helpers.rel_l2(x, g["trace_dyn"][-1]) < 1e-3
+
+
+def test_torch_port_matches_reference(setup):
+    """oracle/torch_port.py (the timed CPU baseline and the stock-bf16 calibration) reproduces the reference's
+    own free-running dynamics-aware trace: same ATen ops in the same order, so fp32 round-off level."""
+    import torch
+    from oracle import torch_port
+    c, sd, g, unet, dif, proj, P = setup
+    tsd = {k: torch.from_numpy(v) for k, v in sd.items()}
+    nz = helpers.normalizer(c)
+    nzt = tuple(torch.from_numpy(np.asarray(a, dtype=np.float32)) for a in (nz.obs_mean, nz.obs_std, nz.action_mean, nz.action_std))
+    projector = dict(P=torch.from_numpy(P), alphas=[float(a) for a in g["alphas"]], nz=nzt, n=c["n"], m=c["m"], H=c["H"])
+    x = torch_port.sample_loop(tsd, torch.from_numpy(np.array(g["x_init"])), torch.from_numpy(g["noise"]),
+                               conditions={0: torch.from_numpy(g["start"])}, projector=projector)
+    assert helpers.rel_l2(x.numpy(), g["trace_dyn"][-1]) < 5e-5
+    x = torch_port.sample_loop(tsd, torch.from_numpy(np.array(g["x_init"])), torch.from_numpy(g["noise"]),
+                               conditions={0: torch.from_numpy(g["start"]), c["H"] - 1: torch.from_numpy(g["goal"])})
+    assert helpers.rel_l2(x.numpy(), g["trace_cond"][-1]) < 5e-5
