@@ -16,9 +16,9 @@
 // shared memory as a 128 x 64 K-major tile with the 128-byte swizzle tcgen05 expects.
 // B operand: pre-packed bf16 weights Wb[n][tap * Cin + c] (K-major), 2-D TMA, same swizzle.
 //
-// Warp roles (192 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = TMEM allocator +
-// single-thread MMA issuer, warps 2-5 = epilogue (TMEM -> registers -> global).  Two TMEM
-// accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+// Warp roles (320 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = TMEM allocator +
+// single-thread MMA issuer, warps 2-9 = two epilogue warpgroups (TMEM -> registers -> global) that take
+// alternate tiles.  Up to four TMEM accumulator stages let the MMAs run ahead of the epilogues.
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
@@ -28,7 +28,8 @@ namespace dad {
 constexpr int TC_BM = 128;       // UMMA M (cta_group::1)
 constexpr int TC_BK = 64;        // bf16 elements per k-block = one 128 B swizzle row
 constexpr int TC_UMMA_K = 16;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WG = 2;     // epilogue warpgroups (4 warps each), alternating tiles
+constexpr int TC_THREADS = 64 + 128 * TC_EPI_WG;
 
 struct ConvTcParams {
   const float *bias;             // [Cout_pad]
@@ -54,12 +55,25 @@ struct TcCfg {
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int B_ALLOC = (B_BYTES + 1023) / 1024 * 1024;
   static constexpr int STAGE_BYTES = A_BYTES + B_ALLOC;
-  static constexpr int STAGES = (BN >= 256) ? 4 : 6;
-  static constexpr int ACC_STAGES = 2;
+  static constexpr int STAGES = (BN >= 256) ? 3 : 5;
+  static constexpr int ACC_STAGES = (BN >= 256) ? 2 : 4;
   static constexpr int TMEM_COLS = (ACC_STAGES * BN <= 32) ? 32 : (ACC_STAGES * BN <= 64) ? 64
                                    : (ACC_STAGES * BN <= 128) ? 128 : (ACC_STAGES * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int BAR_BYTES = 256;
+  // + per-column epilogue parameters (bias, gamma, beta, time bias) for every output channel: 16 B per channel
+  static constexpr int smem_bytes(int cout_pad) { return STAGES * STAGE_BYTES + 1024 /*align slack*/ + BAR_BYTES + 16 * cout_pad; }
 };
+
+// tanh(softplus(y)) = (w - 1) / (w + 1) with w = (1 + e^y)^2, i.e. 1 - 2 / (w + 1): one ex2, one rcp, no clamp
+// (e^y = inf gives rcp(inf) = 0 -> 1).  Absolute error < 1e-6; the output is rounded to bf16 afterwards.
+__device__ __forceinline__ float mish_tc(float y) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(y * 1.4426950408889634f));
+  const float u = 1.f + e;
+  const float w1 = fmaf(u, u, 1.f);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(w1));
+  return y * fmaf(-2.f, r, 1.f);
+}
 
 // GW = GroupNorm group width in columns (0: no GroupNorm/Mish, plain bias epilogue).
 template <int BN, int GW>
@@ -78,7 +92,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   uint64_t *tfull_bar = empty_bar + Cfg::STAGES;
   uint64_t *tempty_bar = tfull_bar + Cfg::ACC_STAGES;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + Cfg::ACC_STAGES);
-  __shared__ float gn_scratch[2][4][2 * 8];     // [tile parity][epilogue warp][sum, sumsq per group]
+  const int cout_pad = p.n_tiles_n * BN;
+  float *s_bias = reinterpret_cast<float *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
+  float *s_gamma = s_bias + cout_pad, *s_beta = s_gamma + cout_pad, *s_tt = s_beta + cout_pad;
+  __shared__ float gn_scratch[TC_EPI_WG][4][2 * 8];   // [warpgroup][epilogue warp][sum, sumsq per group]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.n_tiles_m * p.n_tiles_n;
@@ -96,13 +113,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     }
     for (int s = 0; s < Cfg::ACC_STAGES; ++s) {
       ptx::mbar_init(&tfull_bar[s], 1);
-      ptx::mbar_init(&tempty_bar[s], 4);        // one arrive per epilogue warp
+      ptx::mbar_init(&tempty_bar[s], 4);        // one arrive per warp of the warpgroup that drained it
     }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
     ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     ptx::tmem_relinquish();
+  }
+  if (warp >= 2) {
+    // per-column epilogue parameters -> shared memory, once per CTA (all tiles of this CTA reuse them)
+    const int step = p.ls->step;
+    const float *tt = (p.ttab && !p.ls->t_rows) ? p.ttab + (size_t)step * p.Cout : nullptr;
+    for (int n = threadIdx.x - 64; n < cout_pad; n += TC_THREADS - 64) {
+      const bool in = n < p.Cout;
+      s_bias[n] = p.bias[n];                     // allocated and zero-filled up to Cout_pad
+      if constexpr (GW > 0) {
+        s_gamma[n] = in ? p.gamma[n] : 0.f;
+        s_beta[n] = in ? p.beta[n] : 0.f;
+      }
+      s_tt[n] = (tt && in) ? tt[n] : 0.f;
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -139,8 +170,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
+        const int as = it % Cfg::ACC_STAGES;
+        const uint32_t aphase = (it / Cfg::ACC_STAGES) & 1;
         ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);   // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -164,20 +195,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     __syncwarp();
   } else {
     // ================================ epilogue ====================================
+    // Two warpgroups take alternate tiles so that TMEM/global latency of one hides behind the
+    // arithmetic of the other; each warp owns the TMEM lane quarter (warp % 4).
+    const int wg = (warp - 2) >> 2;
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                  // row of the tile
     const int s_in_tile = r / p.L_out;
     const int l = r - s_in_tile * p.L_out;
     const int L_total = p.L_out * p.out_mul;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    const bool rows_t = (p.ttab != nullptr) && (p.ls->t_rows != nullptr);   // stand-alone forward with per-row timesteps
+    const long long *t_rows = rows_t ? p.ls->t_rows : nullptr;
+    const int lanes = p.L_out < 32 ? p.L_out : 32;
+    const float inv_n = 1.0f / (float)(p.L_out * (GW > 0 ? GW : 1));
+    int it = wg;
+    for (int tile = blockIdx.x + wg * gridDim.x; tile < total_tiles; tile += TC_EPI_WG * gridDim.x, it += TC_EPI_WG) {
       const int tm = tile / p.n_tiles_n, tn = tile - tm * p.n_tiles_n;
       const int n0 = tn * BN;
       const int b = tm * spt + s_in_tile;
       const bool valid = b < p.B;
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      const int as = it % Cfg::ACC_STAGES;
+      const uint32_t aphase = (it / Cfg::ACC_STAGES) & 1;
       const uint32_t t_addr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+      const size_t orow = ((size_t)b * L_total + (size_t)l * p.out_mul + p.out_phase) * p.Cout + n0;
+      // residual of the first column chunk: requested before the accumulator is even ready
+      const bool has_res = (p.residual != nullptr) && valid && !p.out_f32;
+      uint4 rcur[CW / 8];
+      if (has_res) {
+        const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + orow);
+#pragma unroll
+        for (int j = 0; j < CW / 8; ++j) rcur[j] = __ldg(rp + j);
+      }
       ptx::mbar_wait(&tfull_bar[as], aphase);
       ptx::tc_fence_after();
 
@@ -194,12 +241,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < CW; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + c * CW + j));
+            const float4 b4 = *reinterpret_cast<const float4 *>(s_bias + n0 + c * CW + j);
             const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
               const float x = __uint_as_float(v[j + jj]) + bb[jj];
-              constexpr int dummy = 0; (void)dummy;
               const int g = (c * CW + j + jj) / GW;   // compile-time after unrolling
               s1[g] += x;
               s2[g] = fmaf(x, x, s2[g]);
@@ -207,7 +253,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           }
         }
         // reduce across the L rows of this sample (contiguous, aligned lanes)
-        const int lanes = p.L_out < 32 ? p.L_out : 32;
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
           for (int o = lanes >> 1; o > 0; o >>= 1) {
@@ -216,13 +261,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           }
         }
         if (p.L_out > 32) {
-          // a sample spans several epilogue warps: combine through shared memory
-          float *scr = &gn_scratch[it & 1][0][0];
+          // a sample spans several epilogue warps: combine through shared memory (per-warpgroup barrier)
+          float *scr = &gn_scratch[wg][0][0];
+          ptx::named_bar_sync(1 + wg, 128);           // previous tile's readers are done with scr
           if (lane == 0) {
 #pragma unroll
             for (int g = 0; g < NG; ++g) { scr[q * 16 + g] = s1[g]; scr[q * 16 + 8 + g] = s2[g]; }
           }
-          ptx::named_bar_sync(1, 128);
+          ptx::named_bar_sync(1 + wg, 128);
           const int wps = p.L_out / 32;
           const int w0 = (q / wps) * wps;
 #pragma unroll
@@ -232,7 +278,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             s1[g] = a; s2[g] = c2;
           }
         }
-        const float inv_n = 1.0f / (float)(p.L_out * GW);
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
           mean[g] = s1[g] * inv_n;
@@ -243,35 +288,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 
       // ---- pass 2: normalise, Mish, (+ time bias | + residual), convert, store
       const float *trow = nullptr;
-      if (p.ttab) {
-        const long long t = p.ls->t_rows ? (valid ? p.ls->t_rows[b] : 0) : (long long)p.ls->step;
-        trow = p.ttab + (size_t)t * p.Cout + n0;
-      }
-      const size_t orow = ((size_t)b * L_total + (size_t)l * p.out_mul + p.out_phase) * p.Cout + n0;
+      if (rows_t) trow = p.ttab + (size_t)(valid ? t_rows[b] : 0) * p.Cout + n0;
 #pragma unroll
       for (int c = 0; c < NCHUNK; ++c) {
         uint32_t v[32];
         if constexpr (CW == 32) ptx::tmem_ld32(t_addr + c * CW, v); else ptx::tmem_ld16(t_addr + c * CW, v);
+        // residual of the NEXT chunk is requested while this one is processed
+        uint4 rnext[CW / 8];
+        if (has_res && c + 1 < NCHUNK) {
+          const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + orow + (c + 1) * CW);
+#pragma unroll
+          for (int j = 0; j < CW / 8; ++j) rnext[j] = __ldg(rp + j);
+        }
         ptx::tmem_ld_wait();
         float y[CW];
 #pragma unroll
         for (int j = 0; j < CW; j += 4) {
           const int n = n0 + c * CW + j;
-          const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + n));
+          const float4 b4 = *reinterpret_cast<const float4 *>(s_bias + n);
           const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
           if constexpr (GW > 0) {
-            const float4 g4 = __ldg(reinterpret_cast<const float4 *>(p.gamma + n));
-            const float4 e4 = __ldg(reinterpret_cast<const float4 *>(p.beta + n));
+            const float4 g4 = *reinterpret_cast<const float4 *>(s_gamma + n);
+            const float4 e4 = *reinterpret_cast<const float4 *>(s_beta + n);
+            const float4 t4 = *reinterpret_cast<const float4 *>(s_tt + n);
             const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
+            const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
               const int g = (c * CW + j + jj) / GW;
-              const float x = __uint_as_float(v[j + jj]) + bb[jj];
-              y[j + jj] = mish_fast((x - mean[g]) * rstd[g] * gg[jj] + ee[jj]);
+              const float a = rstd[g] * gg[jj];
+              const float bsh = fmaf(bb[jj] - mean[g], a, ee[jj]);
+              y[j + jj] = mish_tc(fmaf(__uint_as_float(v[j + jj]), a, bsh)) + tt[jj];
             }
             if (trow) {
-              const float4 t4 = __ldg(reinterpret_cast<const float4 *>(trow + c * CW + j));
-              y[j] += t4.x; y[j + 1] += t4.y; y[j + 2] += t4.z; y[j + 3] += t4.w;
+              const float4 r4 = __ldg(reinterpret_cast<const float4 *>(trow + c * CW + j));
+              y[j] += r4.x; y[j + 1] += r4.y; y[j + 2] += r4.z; y[j + 3] += r4.w;
             }
           } else {
 #pragma unroll
@@ -285,12 +336,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             for (int j = 0; j < CW; ++j)
               if (n0 + c * CW + j < p.Cout) o[j] = y[j];
           } else {
-            if (p.residual) {
-              const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + orow + c * CW);
+            if (has_res) {
 #pragma unroll
               for (int j = 0; j < CW; j += 8) {
-                const uint4 rv = __ldg(rp + j / 8);
-                const __nv_bfloat162 *r2 = reinterpret_cast<const __nv_bfloat162 *>(&rv);
+                const __nv_bfloat162 *r2 = reinterpret_cast<const __nv_bfloat162 *>(&rcur[j / 8]);
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                   const float2 f = __bfloat1622float2(r2[jj]);
@@ -309,6 +358,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               op[j / 8] = ov;
             }
           }
+        }
+        if (c + 1 < NCHUNK) {
+#pragma unroll
+          for (int j = 0; j < CW / 8; ++j) rcur[j] = rnext[j];
         }
       }
       // release the accumulator stage back to the MMA issuer

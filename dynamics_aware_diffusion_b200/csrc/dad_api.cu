@@ -377,27 +377,33 @@ int finish_tc_op(dad_handle *h, ConvOp &op) {
 template <int BN, int GW>
 int launch_tc(dad_handle *h, const ConvOp &op, const ConvTcParams &p, int grid, cudaStream_t st) {
   auto kern = conv_tc_kernel<BN, GW>;
-  kern<<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(op.tmA1, op.tmA2, op.tmW, p);
+  kern<<<grid, TC_THREADS, TcCfg<BN>::smem_bytes(op.Cout_pad), st>>>(op.tmA1, op.tmA2, op.tmW, p);
   return DAD_OK;
 }
 
 template <int BN, int GW>
-cudaError_t set_tc_attr() {
-  return cudaFuncSetAttribute(conv_tc_kernel<BN, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES);
+cudaError_t set_tc_attr(int max_optin) {
+  // the dynamic size depends on the layer's channel count (per-column epilogue parameters); allow the maximum
+  // (the opt-in limit covers static + dynamic shared memory)
+  cudaFuncAttributes fa{};
+  cudaError_t e = cudaFuncGetAttributes(&fa, conv_tc_kernel<BN, GW>);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(conv_tc_kernel<BN, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              max_optin - (int)fa.sharedSizeBytes);
 }
 
 // Opt-in shared memory sizes are set once at create (never inside a stream capture).
 int set_kernel_attrs(dad_handle *h) {
-  CK(h, (set_tc_attr<64, 8>()));
-  CK(h, (set_tc_attr<128, 16>()));
-  CK(h, (set_tc_attr<128, 32>()));
-  CK(h, (set_tc_attr<128, 64>()));
-  CK(h, (set_tc_attr<128, 128>()));
-  CK(h, (set_tc_attr<256, 256>()));
-  CK(h, (set_tc_attr<16, 0>()));
-  CK(h, (set_tc_attr<32, 0>()));
-  CK(h, (set_tc_attr<64, 0>()));
-  CK(h, (set_tc_attr<128, 0>()));
+  CK(h, (set_tc_attr<64, 8>(h->max_smem_optin)));
+  CK(h, (set_tc_attr<128, 16>(h->max_smem_optin)));
+  CK(h, (set_tc_attr<128, 32>(h->max_smem_optin)));
+  CK(h, (set_tc_attr<128, 64>(h->max_smem_optin)));
+  CK(h, (set_tc_attr<128, 128>(h->max_smem_optin)));
+  CK(h, (set_tc_attr<256, 256>(h->max_smem_optin)));
+  CK(h, (set_tc_attr<16, 0>(h->max_smem_optin)));
+  CK(h, (set_tc_attr<32, 0>(h->max_smem_optin)));
+  CK(h, (set_tc_attr<64, 0>(h->max_smem_optin)));
+  CK(h, (set_tc_attr<128, 0>(h->max_smem_optin)));
   CK(h, cudaFuncSetAttribute(step_project_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   return DAD_OK;
 }
