@@ -2,7 +2,9 @@
 import ctypes
 import os
 
-from .build import LIB_PATH
+from .build import LIB_PATH as _DEFAULT_LIB
+
+LIB_PATH = os.environ.get("DAD_LIB_PATH", _DEFAULT_LIB)      # tuning variants only; default = the in-tree build
 
 DAD_ABI_VERSION = 1
 DAD_MAX_LEVELS = 8

@@ -28,13 +28,15 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    """Compile csrc/*.cu into libdad_b200.so next to this file.  nvcc cross-compiles without a GPU."""
-    if not force and not _stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile csrc/*.cu into libdad_b200.so next to this file.  nvcc cross-compiles without a GPU.
+    `defines` / `out` build a tuning variant under another file name (selected at run time with DAD_LIB_PATH)."""
+    target = out or LIB_PATH
+    if not force and not out and not _stale():
         return LIB_PATH
     cmd = [_nvcc(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
            "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(REPO_ROOT, "include"), "-I", CSRC,
-           "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-o", target] + ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd += ["-Xptxas", "-v"]
         print(" ".join(cmd))
@@ -43,8 +45,10 @@ def build(force=False, verbose=False):
         sys.stdout.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    return LIB_PATH
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-q" not in sys.argv, defines=defs, out=outs[0] if outs else None))

@@ -28,7 +28,13 @@ namespace dad {
 constexpr int TC_BM = 128;       // UMMA M (cta_group::1)
 constexpr int TC_BK = 64;        // bf16 elements per k-block = one 128 B swizzle row
 constexpr int TC_UMMA_K = 16;
-constexpr int TC_EPI_WG = 2;     // epilogue warpgroups (4 warps each), alternating tiles
+#ifndef DAD_TC_EPI_WG
+#define DAD_TC_EPI_WG 2
+#endif
+#ifndef DAD_TC_CW
+#define DAD_TC_CW 32
+#endif
+constexpr int TC_EPI_WG = DAD_TC_EPI_WG;     // epilogue warpgroups (4 warps each), alternating tiles
 constexpr int TC_THREADS = 64 + 128 * TC_EPI_WG;
 
 struct ConvTcParams {
@@ -47,6 +53,8 @@ struct ConvTcParams {
   int taps;
   int tap_j[kMaxTaps], tap_p[kMaxTaps];
   int out_f32;
+  unsigned long long *prof;      // optional cycle counters (DAD_TC_PROF): [wait, pass1, pass2, tiles] summed over epilogue warps
+  int debug;                     // 0 normal; 1 = skip the epilogue arithmetic; 2 = skip TMA + MMA (profiling only, DAD_TC_DEBUG)
 };
 
 template <int BN>
@@ -81,7 +89,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmW, const ConvTcParams p) {
   using Cfg = TcCfg<BN>;
-  constexpr int CW = (BN < 32) ? 16 : 32;       // columns per TMEM load
+  constexpr int CW = (BN < 32) ? 16 : DAD_TC_CW;       // columns per TMEM load
   constexpr int NCHUNK = BN / CW;
   constexpr int NG = (GW > 0) ? BN / GW : 1;    // groups per N-tile
 
@@ -93,8 +101,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   uint64_t *tempty_bar = tfull_bar + Cfg::ACC_STAGES;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + Cfg::ACC_STAGES);
   const int cout_pad = p.n_tiles_n * BN;
-  float *s_bias = reinterpret_cast<float *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
-  float *s_gamma = s_bias + cout_pad, *s_beta = s_gamma + cout_pad, *s_tt = s_beta + cout_pad;
+  // per-column epilogue parameters, interleaved: s_par[col] = {gamma, beta, bias, time bias} (one LDS.128 per column)
+  const uint32_t s_par = ptx::smem_u32(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
   __shared__ float gn_scratch[TC_EPI_WG][4][2 * 8];   // [warpgroup][epilogue warp][sum, sumsq per group]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -127,12 +135,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     const float *tt = (p.ttab && !p.ls->t_rows) ? p.ttab + (size_t)step * p.Cout : nullptr;
     for (int n = threadIdx.x - 64; n < cout_pad; n += TC_THREADS - 64) {
       const bool in = n < p.Cout;
-      s_bias[n] = p.bias[n];                     // allocated and zero-filled up to Cout_pad
+      float g = 0.f, e = 0.f;
       if constexpr (GW > 0) {
-        s_gamma[n] = in ? p.gamma[n] : 0.f;
-        s_beta[n] = in ? p.beta[n] : 0.f;
+        if (in) { g = p.gamma[n]; e = p.beta[n]; }
       }
-      s_tt[n] = (tt && in) ? tt[n] : 0.f;
+      ptx::sts32(s_par + n * 16 + 0, g);
+      ptx::sts32(s_par + n * 16 + 4, e);
+      ptx::sts32(s_par + n * 16 + 8, p.bias[n]);   // allocated and zero-filled up to Cout_pad
+      ptx::sts32(s_par + n * 16 + 12, (tt && in) ? tt[n] : 0.f);
     }
   }
   ptx::tc_fence_before();
@@ -142,7 +152,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    if (lane == 0 && !(p.debug & 2)) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -175,7 +185,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);   // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < ((p.debug & 2) ? 0 : num_kb); ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);      // TMA bytes have landed
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -195,8 +205,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     __syncwarp();
   } else {
     // ================================ epilogue ====================================
-    // Two warpgroups take alternate tiles so that TMEM/global latency of one hides behind the
-    // arithmetic of the other; each warp owns the TMEM lane quarter (warp % 4).
+    // TC_EPI_WG warpgroups take alternate tiles so that the TMEM / shared / global latencies of one hide
+    // behind the arithmetic of the others; each warp owns the TMEM lane quarter (warp % 4).  The column
+    // loops are deliberately NOT unrolled across chunks: the body is ~1K instructions and must stay
+    // resident in the instruction cache while 8-16 warps run it at different phases.
     const int wg = (warp - 2) >> 2;
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                  // row of the tile
@@ -207,8 +219,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     const long long *t_rows = rows_t ? p.ls->t_rows : nullptr;
     const int lanes = p.L_out < 32 ? p.L_out : 32;
     const float inv_n = 1.0f / (float)(p.L_out * (GW > 0 ? GW : 1));
+    constexpr int GPC = (GW > 0 && GW < CW) ? CW / GW : 1;     // GroupNorm groups per column chunk
+    constexpr int CPG = (GW >= CW) ? GW / CW : 1;              // column chunks per GroupNorm group
     int it = wg;
+    long long pc_wait = 0, pc_p1 = 0, pc_p2 = 0, pc_n = 0, pc_t0 = 0, pc_t1 = 0;
     for (int tile = blockIdx.x + wg * gridDim.x; tile < total_tiles; tile += TC_EPI_WG * gridDim.x, it += TC_EPI_WG) {
+      if (p.prof) pc_t0 = clock64();
       const int tm = tile / p.n_tiles_n, tn = tile - tm * p.n_tiles_n;
       const int n0 = tn * BN;
       const int b = tm * spt + s_in_tile;
@@ -218,7 +234,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const uint32_t t_addr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
       const size_t orow = ((size_t)b * L_total + (size_t)l * p.out_mul + p.out_phase) * p.Cout + n0;
       // residual of the first column chunk: requested before the accumulator is even ready
-      const bool has_res = (p.residual != nullptr) && valid && !p.out_f32;
+      const bool has_res = (p.residual != nullptr) && valid && !p.out_f32 && !(p.debug & 8);
       uint4 rcur[CW / 8];
       if (has_res) {
         const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + orow);
@@ -227,69 +243,90 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       }
       ptx::mbar_wait(&tfull_bar[as], aphase);
       ptx::tc_fence_after();
+      if (p.prof) { pc_t1 = clock64(); pc_wait += pc_t1 - pc_t0; pc_t0 = pc_t1; }
+      if (p.debug == 1) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+        continue;
+      }
 
-      float mean[NG], rstd[NG];
-      if constexpr (GW > 0) {
+      float mean_a[NG], rstd_a[NG];               // dynamically indexed -> thread-local memory (L1 resident)
+      if (p.debug & 16) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) { mean_a[g] = 0.f; rstd_a[g] = 1.f; }
+      } else if constexpr (GW > 0) {
         // ---- pass 1: GroupNorm statistics of (conv + bias) over (L rows) x (GW columns)
-        float s1[NG], s2[NG];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) { s1[g] = 0.f; s2[g] = 0.f; }
-#pragma unroll
+        float run1 = 0.f, run2 = 0.f;             // carried across the chunks of a wide group
+#pragma unroll 1
         for (int c = 0; c < NCHUNK; ++c) {
           uint32_t v[32];
           if constexpr (CW == 32) ptx::tmem_ld32(t_addr + c * CW, v); else ptx::tmem_ld16(t_addr + c * CW, v);
+          float s1[GPC], s2[GPC];
+#pragma unroll
+          for (int g = 0; g < GPC; ++g) { s1[g] = 0.f; s2[g] = 0.f; }
+          // parameter loads are issued BEFORE waiting for the TMEM load so that the two latencies overlap
+          const uint32_t sp = s_par + (uint32_t)(n0 + c * CW) * 16u;
+          float bb[CW];
+#pragma unroll
+          for (int j = 0; j < CW; ++j) bb[j] = ptx::lds128(sp + j * 16).z;
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < CW; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4 *>(s_bias + n0 + c * CW + j);
-            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+          for (int j = 0; j < CW; ++j) {
+            const float x = __uint_as_float(v[j]) + bb[j];
+            const int g = (GW < CW) ? j / GW : 0;   // compile-time
+            s1[g] += x;
+            s2[g] = fmaf(x, x, s2[g]);
+          }
+          if constexpr (GW >= CW) {
+            run1 += s1[0];
+            run2 += s2[0];
+            if ((c + 1) % CPG != 0) continue;
+            s1[0] = run1; s2[0] = run2;
+            run1 = 0.f; run2 = 0.f;
+          }
+          // reduce across the L rows of this sample (contiguous, aligned lanes)
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const float x = __uint_as_float(v[j + jj]) + bb[jj];
-              const int g = (c * CW + j + jj) / GW;   // compile-time after unrolling
-              s1[g] += x;
-              s2[g] = fmaf(x, x, s2[g]);
+          for (int g = 0; g < GPC; ++g) {
+            for (int o = lanes >> 1; o > 0; o >>= 1) {
+              s1[g] += __shfl_xor_sync(0xffffffffu, s1[g], o);
+              s2[g] += __shfl_xor_sync(0xffffffffu, s2[g], o);
             }
           }
-        }
-        // reduce across the L rows of this sample (contiguous, aligned lanes)
+          if (p.L_out > 32) {
+            // a sample spans several epilogue warps: combine through shared memory (per-warpgroup barrier)
+            float *scr = &gn_scratch[wg][0][0];
+            ptx::named_bar_sync(1 + wg, 128);           // previous readers are done with scr
+            if (lane == 0) {
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          for (int o = lanes >> 1; o > 0; o >>= 1) {
-            s1[g] += __shfl_xor_sync(0xffffffffu, s1[g], o);
-            s2[g] += __shfl_xor_sync(0xffffffffu, s2[g], o);
+              for (int g = 0; g < GPC; ++g) { scr[q * 16 + g] = s1[g]; scr[q * 16 + 8 + g] = s2[g]; }
+            }
+            ptx::named_bar_sync(1 + wg, 128);
+            const int wps = p.L_out / 32;
+            const int w0 = (q / wps) * wps;
+#pragma unroll
+            for (int g = 0; g < GPC; ++g) {
+              float a = 0.f, c2 = 0.f;
+              for (int w = 0; w < wps; ++w) { a += scr[(w0 + w) * 16 + g]; c2 += scr[(w0 + w) * 16 + 8 + g]; }
+              s1[g] = a; s2[g] = c2;
+            }
           }
-        }
-        if (p.L_out > 32) {
-          // a sample spans several epilogue warps: combine through shared memory (per-warpgroup barrier)
-          float *scr = &gn_scratch[wg][0][0];
-          ptx::named_bar_sync(1 + wg, 128);           // previous tile's readers are done with scr
-          if (lane == 0) {
+          const int g0 = (GW >= CW) ? c / CPG : c * GPC;
 #pragma unroll
-            for (int g = 0; g < NG; ++g) { scr[q * 16 + g] = s1[g]; scr[q * 16 + 8 + g] = s2[g]; }
+          for (int g = 0; g < GPC; ++g) {
+            const float m = s1[g] * inv_n;
+            const float var = fmaxf(s2[g] * inv_n - m * m, 0.f);
+            mean_a[g0 + g] = m;
+            rstd_a[g0 + g] = rsqrtf(var + kGnEps);
           }
-          ptx::named_bar_sync(1 + wg, 128);
-          const int wps = p.L_out / 32;
-          const int w0 = (q / wps) * wps;
-#pragma unroll
-          for (int g = 0; g < NG; ++g) {
-            float a = 0.f, c2 = 0.f;
-            for (int w = 0; w < wps; ++w) { a += scr[(w0 + w) * 16 + g]; c2 += scr[(w0 + w) * 16 + 8 + g]; }
-            s1[g] = a; s2[g] = c2;
-          }
-        }
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          mean[g] = s1[g] * inv_n;
-          const float var = fmaxf(s2[g] * inv_n - mean[g] * mean[g], 0.f);
-          rstd[g] = rsqrtf(var + kGnEps);
         }
       }
 
+      if (p.prof) { pc_t1 = clock64(); pc_p1 += pc_t1 - pc_t0; pc_t0 = pc_t1; }
       // ---- pass 2: normalise, Mish, (+ time bias | + residual), convert, store
       const float *trow = nullptr;
       if (rows_t) trow = p.ttab + (size_t)(valid ? t_rows[b] : 0) * p.Cout + n0;
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < NCHUNK; ++c) {
         uint32_t v[32];
         if constexpr (CW == 32) ptx::tmem_ld32(t_addr + c * CW, v); else ptx::tmem_ld16(t_addr + c * CW, v);
@@ -300,41 +337,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < CW / 8; ++j) rnext[j] = __ldg(rp + j);
         }
-        ptx::tmem_ld_wait();
+        float mg[GPC], rg[GPC];
+        if constexpr (GW > 0) {
+          const int g0 = (GW >= CW) ? c / CPG : c * GPC;
+#pragma unroll
+          for (int g = 0; g < GPC; ++g) { mg[g] = mean_a[g0 + g]; rg[g] = rstd_a[g0 + g]; }
+        }
+        const int nc = n0 + c * CW;
+        const uint32_t sp = s_par + (uint32_t)nc * 16u;
         float y[CW];
+        if constexpr (GW > 0) {
+          // fold (bias, mean, rstd, gamma, beta) into one multiply-add per element while the TMEM load flies
+          float a[CW], bsh[CW], tt[CW];
 #pragma unroll
-        for (int j = 0; j < CW; j += 4) {
-          const int n = n0 + c * CW + j;
-          const float4 b4 = *reinterpret_cast<const float4 *>(s_bias + n);
-          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-          if constexpr (GW > 0) {
-            const float4 g4 = *reinterpret_cast<const float4 *>(s_gamma + n);
-            const float4 e4 = *reinterpret_cast<const float4 *>(s_beta + n);
-            const float4 t4 = *reinterpret_cast<const float4 *>(s_tt + n);
-            const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
-            const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
+          for (int j = 0; j < CW; ++j) {
+            const float4 pr = ptx::lds128(sp + j * 16);       // {gamma, beta, bias, time bias}
+            const int g = (GW < CW) ? j / GW : 0;
+            a[j] = rg[g] * pr.x;
+            bsh[j] = fmaf(pr.z - mg[g], a[j], pr.y);
+            tt[j] = pr.w;
+          }
+          ptx::tmem_ld_wait();
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const int g = (c * CW + j + jj) / GW;
-              const float a = rstd[g] * gg[jj];
-              const float bsh = fmaf(bb[jj] - mean[g], a, ee[jj]);
-              y[j + jj] = mish_tc(fmaf(__uint_as_float(v[j + jj]), a, bsh)) + tt[jj];
-            }
-            if (trow) {
+          for (int j = 0; j < CW; ++j) {
+            const float xn = fmaf(__uint_as_float(v[j]), a[j], bsh[j]);
+            y[j] = ((p.debug & 32) ? xn : mish_tc(xn)) + tt[j];
+          }
+          if (trow) {
+#pragma unroll
+            for (int j = 0; j < CW; j += 4) {
               const float4 r4 = __ldg(reinterpret_cast<const float4 *>(trow + c * CW + j));
               y[j] += r4.x; y[j + 1] += r4.y; y[j + 2] += r4.z; y[j + 3] += r4.w;
             }
-          } else {
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) y[j + jj] = __uint_as_float(v[j + jj]) + bb[jj];
           }
+        } else {
+          float bb[CW];
+#pragma unroll
+          for (int j = 0; j < CW; ++j) bb[j] = ptx::lds128(sp + j * 16).z;
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < CW; ++j) y[j] = __uint_as_float(v[j]) + bb[j];
         }
-        if (valid) {
+        if (valid && (!(p.debug & 4) || y[0] == 123.456f)) {
           if (p.out_f32) {
             float *o = reinterpret_cast<float *>(p.out) + orow + c * CW;
 #pragma unroll
             for (int j = 0; j < CW; ++j)
-              if (n0 + c * CW + j < p.Cout) o[j] = y[j];
+              if (nc + j < p.Cout) o[j] = y[j];
           } else {
             if (has_res) {
 #pragma unroll
@@ -359,15 +408,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             }
           }
         }
-        if (c + 1 < NCHUNK) {
 #pragma unroll
-          for (int j = 0; j < CW / 8; ++j) rcur[j] = rnext[j];
-        }
+        for (int j = 0; j < CW / 8; ++j) rcur[j] = rnext[j];
       }
       // release the accumulator stage back to the MMA issuer
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+      if (p.prof) { pc_p2 += clock64() - pc_t0; pc_n += 1; }
+    }
+    if (p.prof && lane == 0) {
+      atomicAdd(p.prof + 0, (unsigned long long)pc_wait);
+      atomicAdd(p.prof + 1, (unsigned long long)pc_p1);
+      atomicAdd(p.prof + 2, (unsigned long long)pc_p2);
+      atomicAdd(p.prof + 3, (unsigned long long)pc_n);
     }
   }
 

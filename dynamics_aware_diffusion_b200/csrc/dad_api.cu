@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <unordered_map>
@@ -348,6 +349,8 @@ int setup_tc_op(dad_handle *h, ConvOp &op) {
     p.tap_j[t] = (off - ph) / s;
   }
   p.out_f32 = op.head ? 1 : 0;
+  p.debug = getenv("DAD_TC_DEBUG") ? atoi(getenv("DAD_TC_DEBUG")) : 0;
+  p.prof = nullptr;
   p.ls = h->d_ls;
   return DAD_OK;
 }
@@ -1163,10 +1166,25 @@ int dad_time_layer(dad_handle *h, int32_t index, int32_t B, int32_t iters, float
   ls.x = h->d_xtmp;
   int rc = set_loop_state(h, ls, st);
   if (rc) return rc;
-  const ConvOp &op = h->ops[index];
+  ConvOp &op = h->ops[index];
+  unsigned long long *prof = nullptr;
+  if (h->bf16 && getenv("DAD_TC_PROF")) {
+    CK(h, cudaMalloc(&prof, 4 * sizeof(unsigned long long)));
+    CK(h, cudaMemset(prof, 0, 4 * sizeof(unsigned long long)));
+    op.tcp.prof = prof;
+  }
   h->counting = 0;
   rc = time_launches(h, st, iters, ms, [&]() { return h->bf16 ? enqueue_tc(h, op, B, st) : enqueue_f32(h, op, B, st); });
   h->launches += h->counting;
+  if (prof) {
+    unsigned long long v[4];
+    cudaMemcpy(v, prof, sizeof(v), cudaMemcpyDeviceToHost);
+    const double n = v[3] ? (double)v[3] : 1.0;     // warp-tiles
+    fprintf(stderr, "[prof] layer %d %s: per warp-tile cycles: wait %.0f  pass1 %.0f  pass2 %.0f  (warp-tiles %llu over %d launches)\n",
+            index, op.wname.c_str(), v[0] / n, v[1] / n, v[2] / n, v[3], iters + 1);
+    op.tcp.prof = nullptr;
+    cudaFree(prof);
+  }
   return rc;
 }
 
