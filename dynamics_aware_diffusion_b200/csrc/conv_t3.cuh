@@ -1,0 +1,607 @@
+// K1/K2 (v3): stride-1 Conv1d-over-horizon on tcgen05 with ONE activation load per 64-channel block.
+//
+//   replaces  Conv1dBlock (Conv1d k -> GroupNorm(8) -> Mish) + time add + residual add   temporal_unet.py:69-73,117,122
+//             and the 1x1 residual convs                                               temporal_unet.py:103
+//
+// Differences from conv_tc.cuh (the generic path, still used for strided / transposed / head convs):
+//  * POSITION-MAJOR tile rows.  A super-tile is S_t whole samples x L positions (S_t a multiple of 8,
+//    L * S_t = 128 * MH rows).  The activation box for one 64-channel block is fetched ONCE with its halo,
+//    as (L + halo) positions x S_t samples rows of 128 B, ordered position-major by a tensor map whose
+//    dimensions are (channel, sample, position).  Tap t of the convolution is then the SAME shared-memory
+//    tile viewed S_t rows further down: S_t * 128 B is a multiple of the 1024-byte swizzle atom, so the UMMA
+//    descriptor just moves its start address.  The halo rows come back zero-filled from the TMA unit (that is
+//    the conv padding).  L2->SM operand traffic drops from taps x (A + B) to A + taps x B per K block.
+//  * MH = 2 (L = 32): two 128-row accumulators share every weight tile.
+//  * CL = 2: the two CTAs of a cluster work on neighbouring super-tiles of the same N-tile; each loads half of
+//    every weight tile and multicasts it to both (weight traffic per CTA halves again).
+//  * Epilogue: GroupNorm statistics reduced with lane shuffles + one shared-memory exchange per tile; the
+//    normalise / Mish / time-bias / residual arithmetic runs on packed fp32x2 instructions; the bf16 tile goes
+//    through a swizzled shared-memory staging buffer and leaves with a TMA store (the residual arrives the
+//    same way), so global accesses are full lines instead of 16-byte pieces per row.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace dad {
+
+constexpr int T3_BN = 128;
+constexpr int T3_BK = 64;
+constexpr int T3_NB = 4;            // weight-tile ring
+constexpr int T3_THREADS = 320;     // producer, MMA issuer, 2 epilogue warpgroups
+constexpr int T3_STAGE_OUT = 128 * T3_BN * 2;          // 32 KB bf16 staging per epilogue warpgroup
+// MODE: how the CTAs of a launch cooperate
+constexpr int T3_SINGLE = 0;        // one CTA per tile, tcgen05 cta_group::1
+constexpr int T3_MCAST = 1;         // 2-CTA cluster, neighbouring M tiles, weight tiles multicast (cta_group::1)
+constexpr int T3_PAIR = 2;          // 2-CTA cluster, ONE tcgen05 cta_group::2 MMA of M = 256: each CTA holds 128
+                                    // rows of A and half of the weight tile, the leader issues for both
+
+struct ConvT3Params {
+  const float *bias, *gamma, *beta, *ttab;
+  const LoopState *ls;
+  unsigned long long *prof;
+  int B;                     // samples in this launch
+  int L;                     // positions per sample
+  int S_t;                   // samples per super-tile (multiple of 8)
+  int Cout;
+  int n_mst, n_tiles_n;      // M super-tiles, N tiles
+  int kch1, kch2;            // 64-channel blocks of source 1 / 2
+  int taps;
+  int tap_row[kMaxTaps];     // row offset of the tap's view into the haloed tile = (tap_off + halo_lo) * S_t
+  int halo_lo;
+  int a_tx_bytes;            // (L + halo) * S_t * 128: bytes one activation box delivers
+  int a_stage_bytes;         // the same rounded up to 1024
+  int n_a_stages;            // 2..4
+  int b_stage_bytes;         // bytes of weight tile each CTA keeps per K block
+  int has_res;
+  int debug;
+};
+
+struct T3Smem {
+  // byte offsets from the 1024-aligned base
+  int a_ring, b_ring, stage_out, bars, params, scratch, total;
+};
+
+__host__ __device__ inline T3Smem t3_smem_layout(int a_stage_bytes, int n_a, int b_stage_bytes, int cout_pad, int S_t, int ng) {
+  T3Smem s;
+  s.a_ring = 0;
+  s.b_ring = s.a_ring + n_a * a_stage_bytes;
+  s.stage_out = s.b_ring + T3_NB * b_stage_bytes;
+  s.bars = s.stage_out + 2 * T3_STAGE_OUT;
+  s.params = s.bars + 256;
+  s.scratch = s.params + 20 * cout_pad;                           // 16 B per channel (pairs) + 4 B bias
+  s.total = s.scratch + 2 * 4 * S_t * (ng > 0 ? ng : 1) * 8 + 1024 /*alignment slack*/;
+  return s;
+}
+
+// ---- packed fp32x2 helpers (sm_100 FFMA2 / FADD2 / FMUL2) ---------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Mish on a pair: y * (1 - 2 / ((1 + e^y)^2 + 1))
+__device__ __forceinline__ f32x2 mish2(f32x2 y) {
+  float z0, z1;
+  upk2(fmul2(y, pk2(1.4426950408889634f, 1.4426950408889634f)), z0, z1);
+  const f32x2 one = pk2(1.f, 1.f);
+  const f32x2 u = fadd2(pk2(ex2_approx(z0), ex2_approx(z1)), one);
+  float w0, w1;
+  upk2(ffma2(u, u, one), w0, w1);
+  const f32x2 t = ffma2(pk2(rcp_approx(w0), rcp_approx(w1)), pk2(-2.f, -2.f), one);
+  return fmul2(y, t);
+}
+
+template <int GW, int MH, int MODE, int NS>
+__global__ void __launch_bounds__(T3_THREADS, 1)
+conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ CUtensorMap tmO, const ConvT3Params p) {
+  static_assert(NS == 1 || (MODE == T3_PAIR && MH == 1), "256-wide items need the CTA pair and one accumulator half");
+  constexpr int CL = (MODE == T3_SINGLE) ? 1 : 2;
+  constexpr int BN_ITEM = NS * T3_BN;                     // output channels per work item
+  constexpr int ACC = 512 / BN_ITEM;                      // TMEM accumulator stages
+  constexpr int CW = 16;                                  // columns per TMEM load
+  constexpr int NCHUNK = T3_BN / CW;
+  constexpr int NG = (GW > 0) ? T3_BN / GW : 1;           // GroupNorm groups per 128-column sub-tile
+  constexpr int GPC = (GW > 0 && GW < CW) ? CW / GW : 1;  // groups per column chunk
+  constexpr int CPG = (GW >= CW) ? GW / CW : 1;           // chunks per group
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1u);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int n_tiles_n = p.n_tiles_n;                      // items along N (BN_ITEM wide)
+  const int cout_pad = n_tiles_n * BN_ITEM;
+  const T3Smem lay = t3_smem_layout(p.a_stage_bytes, p.n_a_stages, p.b_stage_bytes, cout_pad, p.S_t, NG);
+  const uint32_t s_base = ptx::smem_u32(smem);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + lay.bars);
+  uint64_t *full_a = bars;                 // [4]
+  uint64_t *empty_a = bars + 4;            // [4]
+  uint64_t *full_b = bars + 8;             // [T3_NB]
+  uint64_t *empty_b = bars + 12;           // [T3_NB]
+  uint64_t *tfull = bars + 16;             // [ACC]
+  uint64_t *tempty = bars + 20;            // [ACC]
+  uint64_t *res_bar = bars + 24;           // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 26);
+  const uint32_t s_pair = s_base + lay.params;                      // [cout_pad/2] x {g0,g1,b0,b1 | bias0,bias1,t0,t1}
+  const uint32_t s_bias = s_pair + 16u * (uint32_t)cout_pad;        // [cout_pad] floats
+  const uint32_t s_scr = s_base + lay.scratch;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t cta_rank = 0;
+  if constexpr (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const int kch = p.kch1 + p.kch2;
+  // persistent schedule: work item -> (group of CL consecutive M super-tiles, N item); the CTAs of a cluster
+  // walk the same items in lockstep and take one super-tile of the group each
+  const int n_groups_m = (p.n_mst + CL - 1) / CL;
+  const int total_items = n_groups_m * n_tiles_n;
+  const int first_item = blockIdx.x / CL, item_stride = gridDim.x / CL;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA1);
+    ptx::prefetch_tmap(&tmA2);
+    ptx::prefetch_tmap(&tmW);
+    ptx::prefetch_tmap(&tmR);
+    ptx::prefetch_tmap(&tmO);
+    for (int s = 0; s < 4; ++s) {
+      ptx::mbar_init(&full_a[s], 1);
+      ptx::mbar_init(&empty_a[s], 1);
+    }
+    for (int s = 0; s < T3_NB; ++s) {
+      ptx::mbar_init(&full_b[s], 1);
+      ptx::mbar_init(&empty_b[s], MODE == T3_MCAST ? 2 : 1);   // multicast: both CTAs must have consumed the slot
+    }
+    for (int s = 0; s < ACC; ++s) {
+      ptx::mbar_init(&tfull[s], 1);
+      ptx::mbar_init(&tempty[s], MODE == T3_PAIR ? 8 : 4);     // pair: the epilogue warps of both CTAs
+    }
+    ptx::mbar_init(&res_bar[0], 1);
+    ptx::mbar_init(&res_bar[1], 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    if constexpr (MODE == T3_PAIR) { ptx::tmem_alloc_2sm(tmem_slot, 512); ptx::tmem_relinquish_2sm(); }
+    else { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+  }
+  if (warp >= 2) {
+    const int step = p.ls->step;
+    const float *tt = (p.ttab && !p.ls->t_rows) ? p.ttab + (size_t)step * p.Cout : nullptr;
+    for (int n = threadIdx.x - 64; n < cout_pad; n += T3_THREADS - 64) {
+      const bool in = n < p.Cout;
+      float g = 0.f, e = 0.f;
+      if constexpr (GW > 0) {
+        if (in) { g = p.gamma[n]; e = p.beta[n]; }
+      }
+      const float bi = in ? p.bias[n] : 0.f;
+      const float tv = (tt && in) ? tt[n] : 0.f;
+      const uint32_t pb = s_pair + (uint32_t)(n >> 1) * 32u + (uint32_t)(n & 1) * 4u;
+      ptx::sts32(pb + 0, g);
+      ptx::sts32(pb + 8, e);
+      ptx::sts32(pb + 16, bi);
+      ptx::sts32(pb + 24, tv);
+      ptx::sts32(s_bias + (uint32_t)n * 4u, bi);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if constexpr (CL > 1) ptx::cluster_sync();      // the peer's barriers exist before anything is signalled at them
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0 && !(p.debug & 2)) {
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      // pair mode: both CTAs' loads complete on the LEADER's full barriers (the MMA issuer lives there)
+      const uint32_t lead_full_a = (MODE == T3_PAIR) ? ptx::mapa(ptx::smem_u32(&full_a[0]), 0) : 0;
+      const uint32_t lead_full_b = (MODE == T3_PAIR) ? ptx::mapa(ptx::smem_u32(&full_b[0]), 0) : 0;
+      for (int item = first_item; item < total_items; item += item_stride) {
+        const int gm = item / n_tiles_n, tn = item - gm * n_tiles_n;
+        const int tm = gm * CL + (int)cta_rank;
+        const int b0 = tm * p.S_t, n0 = tn * BN_ITEM;
+        for (int ch = 0; ch < kch; ++ch) {
+          // one haloed activation box per 64-channel block, shared by all taps
+          ptx::mbar_wait(&empty_a[sa], pha ^ 1);
+          uint8_t *dst = smem + lay.a_ring + sa * p.a_stage_bytes;
+          const CUtensorMap *am = (ch < p.kch1) ? &tmA1 : &tmA2;
+          const int c0 = (ch < p.kch1 ? ch : ch - p.kch1) * T3_BK;
+          if (p.debug & 64) {
+            if (MODE != T3_PAIR || cta_rank == 0) ptx::mbar_arrive(&full_a[sa]);   // profiling: MMAs without TMA
+          } else if constexpr (MODE == T3_PAIR) {
+            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_a[sa], 2u * (uint32_t)p.a_tx_bytes);
+            ptx::tma_load_3d_2sm(dst, am, lead_full_a + 8u * sa, c0, b0, -p.halo_lo);
+          } else {
+            ptx::mbar_arrive_expect_tx(&full_a[sa], (uint32_t)p.a_tx_bytes);
+            ptx::tma_load_3d(dst, am, &full_a[sa], c0, b0, -p.halo_lo);
+          }
+          if (++sa == p.n_a_stages) { sa = 0; pha ^= 1; }
+          for (int t = 0; t < p.taps; ++t) {
+            ptx::mbar_wait(&empty_b[sb], phb ^ 1);
+            uint8_t *wdst = smem + lay.b_ring + sb * p.b_stage_bytes;
+            const int k0 = (t * kch + ch) * T3_BK;
+            if (p.debug & 64) {
+              if (MODE != T3_PAIR || cta_rank == 0) ptx::mbar_arrive(&full_b[sb]);
+            } else if constexpr (MODE == T3_SINGLE) {
+              ptx::mbar_arrive_expect_tx(&full_b[sb], (uint32_t)p.b_stage_bytes);
+              ptx::tma_load_2d(wdst, &tmW, &full_b[sb], k0, n0);
+            } else if constexpr (MODE == T3_MCAST) {
+              // this CTA fetches rows [rank*64, rank*64+64) of the weight tile for the whole cluster
+              ptx::mbar_arrive_expect_tx(&full_b[sb], (uint32_t)p.b_stage_bytes);
+              ptx::tma_load_2d_mc(wdst + cta_rank * (p.b_stage_bytes / 2), &tmW, &full_b[sb], k0,
+                                  n0 + (int)cta_rank * (BN_ITEM / 2), MC_MASK);
+            } else {
+              // pair: this CTA keeps its half of the item's output channels; the MMA reads both halves
+              if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_b[sb], 2u * (uint32_t)p.b_stage_bytes);
+              ptx::tma_load_2d_2sm(wdst, &tmW, lead_full_b + 8u * sb, k0, n0 + (int)cta_rank * (BN_ITEM / 2));
+            }
+            if (++sb == T3_NB) { sb = 0; phb ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    // One thread feeds the tensor core (the pair leader's, in pair mode); descriptors advance by adding constants.
+    if (lane == 0 && (MODE != T3_PAIR || cta_rank == 0)) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(MODE == T3_PAIR ? 256 : 128, BN_ITEM);
+      const uint64_t dconst = ptx::make_smem_desc_sw128(0);
+      const uint32_t a_lo0 = ((s_base + lay.a_ring) >> 4), a_lo_step = (uint32_t)p.a_stage_bytes >> 4;
+      const uint32_t b_lo0 = ((s_base + lay.b_ring) >> 4), b_lo_step = (uint32_t)p.b_stage_bytes >> 4;
+      const uint32_t tap_step = p.taps > 1 ? (uint32_t)(p.tap_row[1] - p.tap_row[0]) * 8u : 0u;   // rows * 128 B >> 4
+      const uint32_t tap_first = (uint32_t)p.tap_row[0] * 8u;
+      const int n_taps = p.taps, n_a = p.n_a_stages;
+      const bool run = !(p.debug & 2);
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      int it = 0;
+      for (int item = first_item; item < total_items; item += item_stride, ++it) {
+        uint32_t d_tmem[MH];
+#pragma unroll
+        for (int h = 0; h < MH; ++h) {
+          const int u = it * MH + h;
+          const int as = u % ACC;
+          ptx::mbar_wait(&tempty[as], ((u / ACC) & 1) ^ 1);     // epilogue has drained this accumulator
+          d_tmem[h] = tmem_base + as * BN_ITEM;
+        }
+        ptx::tc_fence_after();
+        if (run) {
+          for (int ch = 0; ch < kch; ++ch) {
+            ptx::mbar_wait(&full_a[sa], pha);
+            uint64_t da = dconst | (uint64_t)(a_lo0 + sa * a_lo_step + tap_first);
+            for (int t = 0; t < n_taps; ++t) {
+              ptx::mbar_wait(&full_b[sb], phb);
+              ptx::tc_fence_after();
+              const uint64_t db = dconst | (uint64_t)(b_lo0 + sb * b_lo_step);
+              const uint32_t acc_kb = (ch | t) != 0;     // the first K block of an item overwrites the accumulator
+#pragma unroll
+              for (int h = 0; h < MH; ++h) {
+                // tap t = the same tile viewed tap_row rows further down (a multiple of the 1024 B swizzle atom)
+#pragma unroll
+                for (int k = 0; k < T3_BK / 16; ++k) {
+                  const uint32_t acc = (k != 0) ? 1u : acc_kb;
+                  if constexpr (MODE == T3_PAIR)
+                    ptx::umma_bf16_2sm(d_tmem[h], da + (uint64_t)(h * 1024 + 2 * k), db + (uint64_t)(2 * k), idesc, acc);
+                  else
+                    ptx::umma_bf16(d_tmem[h], da + (uint64_t)(h * 1024 + 2 * k), db + (uint64_t)(2 * k), idesc, acc);
+                }
+              }
+              if constexpr (MODE == T3_SINGLE) ptx::umma_commit(&empty_b[sb]);
+              else if constexpr (MODE == T3_MCAST) ptx::umma_commit_mc(&empty_b[sb], MC_MASK);
+              else ptx::umma_commit_2sm_mc(&empty_b[sb], MC_MASK);
+              if (++sb == T3_NB) { sb = 0; phb ^= 1; }
+              da += tap_step;
+            }
+            if constexpr (MODE == T3_PAIR) ptx::umma_commit_2sm_mc(&empty_a[sa], MC_MASK);
+            else ptx::umma_commit(&empty_a[sa]);
+            if (++sa == n_a) { sa = 0; pha ^= 1; }
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < MH; ++h) {
+          if constexpr (MODE == T3_PAIR) ptx::umma_commit_2sm_mc(&tfull[(it * MH + h) % ACC], MC_MASK);
+          else ptx::umma_commit(&tfull[(it * MH + h) % ACC]);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================ epilogue ====================================
+    const int wg = (warp - 2) >> 2;
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                  // row within a 128-row half-tile
+    const int s_smp = r % p.S_t;                  // sample within the super-tile (position-major rows)
+    const int pos_per_half = 128 / p.S_t;
+    const bool elected = (threadIdx.x - 64) % 128 == 0;
+    const float inv_n = 1.0f / (float)(p.L * (GW > 0 ? GW : 1));
+    uint8_t *stg_ptr = smem + lay.stage_out + wg * T3_STAGE_OUT;
+    const uint32_t stg = s_base + lay.stage_out + wg * T3_STAGE_OUT;         // [2 boxes][128 rows][128 B], swizzled
+    const uint32_t scr = s_scr + (uint32_t)wg * (4u * p.S_t * NG * 8u);      // [4 warps][S_t][NG] x (sum, sumsq)
+    const uint32_t row_off = (uint32_t)r * 128u;
+    const uint32_t swz = (uint32_t)(r & 7);
+    const bool rows_t = (p.ttab != nullptr) && (p.ls->t_rows != nullptr);
+    const long long *t_rows = rows_t ? p.ls->t_rows : nullptr;
+    const uint32_t tempty0 = (MODE == T3_PAIR) ? ptx::mapa(ptx::smem_u32(&tempty[0]), 0) : ptx::smem_u32(&tempty[0]);
+    uint32_t res_phase = 0;
+    long long pc_wait = 0, pc_p1 = 0, pc_p2 = 0, pc_n = 0, pc_t0 = 0, pc_t1 = 0;
+
+    // Residual tiles travel through the staging buffer: the box for unit (item, ns, h) is requested as soon as
+    // the previous unit's store has finished reading the buffer.
+    auto request_residual = [&](int item, int ns, int h) {
+      const int gm = item / n_tiles_n, tn = item - gm * n_tiles_n;
+      const int tm = gm * CL + (int)cta_rank;
+      const int ch0 = tn * BN_ITEM + ns * T3_BN;
+      ptx::mbar_arrive_expect_tx(&res_bar[wg], T3_STAGE_OUT);
+      ptx::tma_load_3d(stg_ptr, &tmR, &res_bar[wg], ch0, tm * p.S_t, h * pos_per_half);
+      ptx::tma_load_3d(stg_ptr + 16384, &tmR, &res_bar[wg], ch0 + 64, tm * p.S_t, h * pos_per_half);
+    };
+    auto release_acc = [&](int as) {
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (MODE == T3_PAIR) ptx::mbar_arrive_cluster(tempty0 + 8u * as);
+        else ptx::mbar_arrive(&tempty[as]);
+      }
+    };
+
+    if (p.has_res && elected && first_item + wg * item_stride < total_items) request_residual(first_item + wg * item_stride, 0, 0);
+
+    int it = wg;
+    for (int item = first_item + wg * item_stride; item < total_items; item += 2 * item_stride, it += 2) {
+      if (p.prof) pc_t0 = clock64();
+      const int gm = item / n_tiles_n, tn = item - gm * n_tiles_n;
+      const int tm = gm * CL + (int)cta_rank;
+      const int b0 = tm * p.S_t;
+      const bool tile_ok = tm < p.n_mst;
+      const int nitem = item + 2 * item_stride;
+      uint32_t t_addr[MH];
+#pragma unroll
+      for (int h = 0; h < MH; ++h) {
+        const int u = it * MH + h;
+        const int as = u % ACC;
+        ptx::mbar_wait(&tfull[as], (u / ACC) & 1);
+        t_addr[h] = tmem_base + as * BN_ITEM + ((uint32_t)(q * 32) << 16);
+      }
+      ptx::tc_fence_after();
+      if (p.prof) { pc_t1 = clock64(); pc_wait += pc_t1 - pc_t0; pc_t0 = pc_t1; }
+      if ((p.debug & 1) || !tile_ok) {
+        // nothing to write for this super-tile: consume the residual that was prefetched for it and move on
+        if (p.has_res) { ptx::mbar_wait(&res_bar[wg], res_phase); res_phase ^= 1; }
+#pragma unroll
+        for (int h = 0; h < MH; ++h) release_acc((it * MH + h) % ACC);
+        ptx::named_bar_sync(1 + wg, 128);
+        if (p.has_res && elected && nitem < total_items) request_residual(nitem, 0, 0);
+        continue;
+      }
+
+#pragma unroll 1
+      for (int ns = 0; ns < NS; ++ns) {
+        const int n0 = tn * BN_ITEM + ns * T3_BN;
+        const uint32_t col0 = (uint32_t)(ns * T3_BN);
+        if constexpr (GW > 0) {
+          // ---- pass 1: GroupNorm statistics of (conv + bias) over the L positions x GW channels of each sample.
+          // This thread's rows (one per half) belong to ONE sample; lanes with equal (lane % S_t) share it.
+          f32x2 run1 = pk2(0.f, 0.f), run2 = pk2(0.f, 0.f);
+#pragma unroll 1
+          for (int c = 0; c < NCHUNK; ++c) {
+            f32x2 s1[GPC], s2[GPC];
+#pragma unroll
+            for (int g = 0; g < GPC; ++g) { s1[g] = pk2(0.f, 0.f); s2[g] = pk2(0.f, 0.f); }
+            const uint32_t sb = s_bias + (uint32_t)(n0 + c * CW) * 4u;
+            f32x2 bb[CW / 2];
+#pragma unroll
+            for (int j = 0; j < CW / 4; ++j) {
+              const float4 b4 = ptx::lds128(sb + j * 16);
+              bb[2 * j] = pk2(b4.x, b4.y);
+              bb[2 * j + 1] = pk2(b4.z, b4.w);
+            }
+#pragma unroll
+            for (int h = 0; h < MH; ++h) {
+              uint32_t v[32];
+              ptx::tmem_ld16(t_addr[h] + col0 + c * CW, v);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < CW / 2; ++j) {
+                const f32x2 x = fadd2(pk2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bb[j]);
+                const int g = (GW < CW) ? (2 * j) / GW : 0;       // compile-time (GW is even)
+                s1[g] = fadd2(s1[g], x);
+                s2[g] = ffma2(x, x, s2[g]);
+              }
+            }
+            if constexpr (GW >= CW) {
+              run1 = fadd2(run1, s1[0]);
+              run2 = fadd2(run2, s2[0]);
+              if ((c + 1) % CPG != 0) continue;
+              s1[0] = run1; s2[0] = run2;
+              run1 = pk2(0.f, 0.f); run2 = pk2(0.f, 0.f);
+            }
+            const int g0 = (GW >= CW) ? c / CPG : c * GPC;
+#pragma unroll
+            for (int g = 0; g < GPC; ++g) {
+              float a0, a1, q0, q1;
+              upk2(s1[g], a0, a1);
+              upk2(s2[g], q0, q1);
+              float t1 = a0 + a1, t2 = q0 + q1;
+              for (int o = p.S_t; o < 32; o <<= 1) {
+                t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+                t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+              }
+              if (lane < p.S_t) ptx::sts64(scr + (uint32_t)((q * p.S_t + lane) * NG + g0 + g) * 8u, t1, t2);
+            }
+          }
+        }
+        // the staging buffer is free again once the previous store has read it; the elected thread checked that
+        // before it prefetched this unit's residual (or checks it here when there is none)
+        if (!p.has_res && elected) ptx::bulk_wait_read0();
+        ptx::named_bar_sync(1 + wg, 128);          // statistics exchanged, staging buffer reusable
+        if (p.prof) { pc_t1 = clock64(); pc_p1 += pc_t1 - pc_t0; pc_t0 = pc_t1; }
+
+        // ---- pass 2: normalise, Mish, (+ time bias | + residual), convert, stage, TMA store
+#pragma unroll 1
+        for (int h = 0; h < MH; ++h) {
+          if (p.has_res) { ptx::mbar_wait(&res_bar[wg], res_phase); res_phase ^= 1; }
+          const float *trow = nullptr;
+          if (rows_t) {
+            const int b = b0 + s_smp;
+            trow = p.ttab + (size_t)(b < p.B ? t_rows[b] : 0) * p.Cout + n0;
+          }
+#pragma unroll 1
+          for (int c = 0; c < NCHUNK; ++c) {
+            uint32_t v[32];
+            ptx::tmem_ld16(t_addr[h] + col0 + c * CW, v);
+            const int nc = n0 + c * CW;
+            const uint32_t sp = s_pair + (uint32_t)(nc >> 1) * 32u;
+            f32x2 y[CW / 2];
+            if constexpr (GW > 0) {
+              f32x2 rg2[GPC], nm2[GPC];
+              const int g0 = (GW >= CW) ? c / CPG : c * GPC;
+#pragma unroll
+              for (int g = 0; g < GPC; ++g) {
+                float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                  const float2 pr = ptx::lds64(scr + (uint32_t)((w * p.S_t + s_smp) * NG + g0 + g) * 8u);
+                  t1 += pr.x;
+                  t2 += pr.y;
+                }
+                const float m = t1 * inv_n;
+                const float var = fmaxf(t2 * inv_n - m * m, 0.f);
+                const float rs = rsqrtf(var + kGnEps);
+                rg2[g] = pk2(rs, rs);
+                nm2[g] = pk2(-m, -m);
+              }
+              f32x2 a2[CW / 2], bsh[CW / 2], tt2[CW / 2];
+#pragma unroll
+              for (int j = 0; j < CW / 2; ++j) {
+                const float4 p1 = ptx::lds128(sp + j * 32);          // {gamma0, gamma1, beta0, beta1}
+                const float4 p2 = ptx::lds128(sp + j * 32 + 16);     // {bias0, bias1, tt0, tt1}
+                const int g = (GW < CW) ? (2 * j) / GW : 0;
+                a2[j] = fmul2(pk2(p1.x, p1.y), rg2[g]);
+                bsh[j] = ffma2(fadd2(pk2(p2.x, p2.y), nm2[g]), a2[j], pk2(p1.z, p1.w));
+                tt2[j] = pk2(p2.z, p2.w);
+              }
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < CW / 2; ++j) {
+                const f32x2 xn = ffma2(pk2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), a2[j], bsh[j]);
+                y[j] = fadd2((p.debug & 32) ? xn : mish2(xn), tt2[j]);
+              }
+              if (trow) {
+#pragma unroll
+                for (int j = 0; j < CW / 2; ++j) {
+                  const float2 r2 = __ldg(reinterpret_cast<const float2 *>(trow + c * CW + 2 * j));
+                  y[j] = fadd2(y[j], pk2(r2.x, r2.y));
+                }
+              }
+            } else {
+              f32x2 bb[CW / 2];
+#pragma unroll
+              for (int j = 0; j < CW / 2; ++j) {
+                const float4 p2 = ptx::lds128(sp + j * 32 + 16);
+                bb[j] = pk2(p2.x, p2.y);
+              }
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < CW / 2; ++j)
+                y[j] = fadd2(pk2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bb[j]);
+            }
+            // this thread's 16 columns = two 16-byte pieces of its row in the swizzled staging box
+            const uint32_t box = stg + (uint32_t)((c * CW) >> 6) * 16384u + row_off;
+            const uint32_t pc0 = (uint32_t)(((c * CW) & 63) >> 3);
+            const uint32_t ad0 = box + (((pc0) ^ swz) << 4), ad1 = box + (((pc0 + 1) ^ swz) << 4);
+            if (p.has_res) {
+              const uint4 r0 = ptx::lds128u(ad0), r1 = ptx::lds128u(ad1);
+              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int j = 0; j < CW / 2; ++j)
+                y[j] = fadd2(y[j], pk2(__uint_as_float(rw[j] << 16), __uint_as_float(rw[j] & 0xffff0000u)));
+            }
+            uint32_t ow[CW / 2];
+#pragma unroll
+            for (int j = 0; j < CW / 2; ++j) {
+              float lo, hi;
+              upk2(y[j], lo, hi);
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(ow[j]) : "f"(hi), "f"(lo));
+            }
+            ptx::sts128u(ad0, make_uint4(ow[0], ow[1], ow[2], ow[3]));
+            ptx::sts128u(ad1, make_uint4(ow[4], ow[5], ow[6], ow[7]));
+          }
+          // accumulator h is drained once its last sub-tile has been read: hand it back to the MMA issuer
+          if (ns == NS - 1) release_acc((it * MH + h) % ACC);
+          // staged tile -> global with a TMA store (rows of samples >= B land in workspace padding)
+          ptx::fence_proxy_async();
+          ptx::named_bar_sync(1 + wg, 128);
+          // the unit that uses the staging buffer next
+          int nx_item = item, nx_ns = ns, nx_h = h + 1;
+          if (nx_h == MH) { nx_h = 0; if (++nx_ns == NS) { nx_ns = 0; nx_item = nitem; } }
+          const bool same_item = nx_item == item;
+          if (elected) {
+            if (!(p.debug & 4)) {
+              ptx::tma_store_3d(&tmO, stg, n0, b0, h * pos_per_half);
+              ptx::tma_store_3d(&tmO, stg + 16384, n0 + 64, b0, h * pos_per_half);
+            }
+            ptx::bulk_commit();
+            if (p.has_res && nx_item < total_items) {
+              ptx::bulk_wait_read0();
+              request_residual(nx_item, nx_ns, nx_h);
+            }
+          }
+          // without a residual: the next pass 2 of this item must not overwrite the buffer while it is being read
+          // (across items the wait happens right before the statistics barrier)
+          if (!p.has_res && same_item && MH > 1 && nx_ns == ns) {
+            if (elected) ptx::bulk_wait_read0();
+            ptx::named_bar_sync(1 + wg, 128);
+          }
+        }
+      }
+      if (p.prof) { pc_p2 += clock64() - pc_t0; pc_n += 1; }
+    }
+    if (elected) ptx::bulk_wait0();               // all stores of this warpgroup have landed before the CTA exits
+    if (p.prof && lane == 0) {
+      atomicAdd(p.prof + 0, (unsigned long long)pc_wait);
+      atomicAdd(p.prof + 1, (unsigned long long)pc_p1);
+      atomicAdd(p.prof + 2, (unsigned long long)pc_p2);
+      atomicAdd(p.prof + 3, (unsigned long long)pc_n);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if constexpr (CL > 1) ptx::cluster_sync();      // no CTA leaves while its peer may still signal or read it
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    if constexpr (MODE == T3_PAIR) ptx::tmem_dealloc_2sm(tmem_base, 512);
+    else ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace dad

@@ -32,7 +32,7 @@ constexpr int TC_UMMA_K = 16;
 #define DAD_TC_EPI_WG 2
 #endif
 #ifndef DAD_TC_CW
-#define DAD_TC_CW 32
+#define DAD_TC_CW 16
 #endif
 constexpr int TC_EPI_WG = DAD_TC_EPI_WG;     // epilogue warpgroups (4 warps each), alternating tiles
 constexpr int TC_THREADS = 64 + 128 * TC_EPI_WG;

@@ -15,6 +15,7 @@
 #include "dad_b200.h"
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "conv_t3.cuh"
 #include "kernels_f32.cuh"
 #include "step_kernel.cuh"
 
@@ -47,6 +48,11 @@ struct ConvOp {
   int BN = 0, GW = 0;
   CUtensorMap tmA1, tmA2, tmW;
   ConvTcParams tcp{};
+  // v3 path (conv_t3.cuh): stride-1 convs with position-major tiles
+  bool t3 = false;
+  int t3_MH = 1, t3_mode = 0, t3_NS = 1, t3_smem = 0;
+  CUtensorMap t3A1, t3A2, t3W, t3R, t3O;
+  ConvT3Params t3p{};
 };
 
 struct TimeBlock {
@@ -377,6 +383,147 @@ int finish_tc_op(dad_handle *h, ConvOp &op) {
   return DAD_OK;
 }
 
+// ---- v3 path ---------------------------------------------------------------------------------------
+int make_tmap_raw(dad_handle *h, CUtensorMap *m, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
+                  const cuuint32_t *box, const char *what) {
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) DAD_FAIL(h, DAD_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+  return DAD_OK;
+}
+
+// (channel, sample, position) view of a channels-last activation: position-major boxes
+int make_t3_act_tmap(dad_handle *h, CUtensorMap *m, int act, int box_s, int box_l, const char *what) {
+  const Act &a = h->acts[act];
+  cuuint64_t dims[3] = {(cuuint64_t)a.C, (cuuint64_t)h->cfg.max_batch, (cuuint64_t)a.L};
+  cuuint64_t strides[2] = {(cuuint64_t)a.L * a.C * 2, (cuuint64_t)a.C * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_s, (cuuint32_t)box_l};
+  return make_tmap_raw(h, m, act_ptr(h, act), 3, dims, strides, box, what);
+}
+
+bool t3_eligible(const dad_handle *h, const ConvOp &op) {
+  const ConvGeom &g = op.g;
+  if (getenv("DAD_T3") && atoi(getenv("DAD_T3")) == 0) return false;
+  if (op.head || op.transposed || g.in_stride != 1 || g.out_mul != 1) return false;
+  if (g.Cout % T3_BN || g.C1 % 64 || g.C2 % 64) return false;
+  if (!(g.L_out == 4 || g.L_out == 8 || g.L_out == 16 || g.L_out == 32)) return false;
+  if (!op.gname.empty()) {
+    const int gw = g.Cout / kGroups;
+    if (!(gw == 16 || gw == 32 || gw == 64 || gw == 128)) return false;
+  }
+  (void)h;
+  return true;
+}
+
+int setup_t3_op(dad_handle *h, ConvOp &op) {
+  const ConvGeom &g = op.g;
+  ConvT3Params &p = op.t3p;
+  const int L = g.L_out;
+  op.t3_MH = (L == 32) ? 2 : 1;
+  const int S_t = 128 * op.t3_MH / L;
+  int lo = 0, hi = 0;
+  for (int t = 0; t < g.taps; ++t) { lo = std::min(lo, g.tap_off[t]); hi = std::max(hi, g.tap_off[t]); }
+  p.halo_lo = -lo;
+  const int box_l = L + hi - lo;
+  p.a_tx_bytes = box_l * S_t * 128;
+  p.a_stage_bytes = (p.a_tx_bytes + 1023) / 1024 * 1024;
+  for (int t = 0; t < g.taps; ++t) p.tap_row[t] = (g.tap_off[t] - lo) * S_t;
+  p.L = L;
+  p.S_t = S_t;
+  p.Cout = g.Cout;
+  p.kch1 = g.C1 / 64;
+  p.kch2 = g.C2 / 64;
+  p.taps = g.taps;
+  p.has_res = op.res >= 0 ? 1 : 0;
+  p.debug = getenv("DAD_TC_DEBUG") ? atoi(getenv("DAD_TC_DEBUG")) : 0;
+  p.prof = nullptr;
+  p.ls = h->d_ls;
+  // cooperation mode: CTA pairs (cta_group::2) by default, 256-wide items where the layer allows it
+  op.t3_mode = getenv("DAD_T3_MODE") ? atoi(getenv("DAD_T3_MODE")) : T3_PAIR;
+  if (op.t3_mode < 0 || op.t3_mode > 2) op.t3_mode = T3_PAIR;
+  const int want_ns = getenv("DAD_T3_NS") ? atoi(getenv("DAD_T3_NS")) : 2;
+  op.t3_NS = (op.t3_mode == T3_PAIR && op.t3_MH == 1 && g.Cout % 256 == 0 && want_ns == 2) ? 2 : 1;
+  p.n_tiles_n = g.Cout / (T3_BN * op.t3_NS);
+  p.b_stage_bytes = op.t3_mode == T3_PAIR ? op.t3_NS * 8192 : 16384;
+  const int ng = op.GW > 0 ? T3_BN / op.GW : 1;
+  int na = 4;
+  for (; na >= 2; --na) {
+    op.t3_smem = t3_smem_layout(p.a_stage_bytes, na, p.b_stage_bytes, g.Cout, S_t, ng).total;
+    if (op.t3_smem <= h->max_smem_optin) break;
+  }
+  if (na < 2) return DAD_ERR_INVALID;     // caller falls back to the generic path
+  p.n_a_stages = na;
+  return DAD_OK;
+}
+
+int finish_t3_op(dad_handle *h, ConvOp &op) {
+  const ConvGeom &g = op.g;
+  ConvT3Params &p = op.t3p;
+  const int box_l = p.a_tx_bytes / (p.S_t * 128);
+  int rc = make_t3_act_tmap(h, &op.t3A1, op.in1, p.S_t, box_l, "activation");
+  if (rc) return rc;
+  if ((rc = make_t3_act_tmap(h, &op.t3A2, op.in2 >= 0 ? op.in2 : op.in1, p.S_t, box_l, "activation 2"))) return rc;
+  const cuuint64_t K = (cuuint64_t)g.taps * op.Cin_store;
+  cuuint64_t dims[2] = {K, (cuuint64_t)op.Cout_pad};
+  cuuint64_t strides[1] = {K * 2};
+  const int wrows = op.t3_mode == T3_SINGLE ? 128 : op.t3_mode == T3_MCAST ? 64 : 64 * op.t3_NS;
+  cuuint32_t box[2] = {64, (cuuint32_t)wrows};
+  if ((rc = make_tmap_raw(h, &op.t3W, op.w_b16, 2, dims, strides, box, "weights"))) return rc;
+  const int pph = 128 / p.S_t;
+  if ((rc = make_t3_act_tmap(h, &op.t3O, op.out, p.S_t, pph, "output"))) return rc;
+  if ((rc = make_t3_act_tmap(h, &op.t3R, op.res >= 0 ? op.res : op.out, p.S_t, pph, "residual"))) return rc;
+  p.bias = op.bias;
+  p.gamma = op.gamma;
+  p.beta = op.beta;
+  p.ttab = op.tblock >= 0 ? h->tblocks[op.tblock].tab : nullptr;
+  return DAD_OK;
+}
+
+template <int GW, int MH, int MODE, int NS>
+cudaError_t set_t3_attr(int max_optin) {
+  return cudaFuncSetAttribute(conv_t3_kernel<GW, MH, MODE, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+}
+
+template <int GW, int MH, int MODE, int NS>
+int launch_t3(dad_handle *h, const ConvOp &op, const ConvT3Params &p, int grid, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(T3_THREADS);
+  cfg.dynamicSmemBytes = (size_t)op.t3_smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = MODE == T3_SINGLE ? 1 : 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_t3_kernel<GW, MH, MODE, NS>, op.t3A1, op.t3A2, op.t3W, op.t3R, op.t3O, p);
+  if (e != cudaSuccess) DAD_FAIL(h, DAD_ERR_CUDA, "conv_t3 launch failed: %s", cudaGetErrorString(e));
+  return DAD_OK;
+}
+
+#define T3_FOR_EACH_SHAPE(X, gw) X(gw, 1, 0, 1) X(gw, 2, 0, 1) X(gw, 1, 1, 1) X(gw, 2, 1, 1) X(gw, 1, 2, 1) X(gw, 2, 2, 1) X(gw, 1, 2, 2)
+#define T3_FOR_EACH(X) T3_FOR_EACH_SHAPE(X, 0) T3_FOR_EACH_SHAPE(X, 16) T3_FOR_EACH_SHAPE(X, 32) T3_FOR_EACH_SHAPE(X, 64) T3_FOR_EACH_SHAPE(X, 128)
+
+int enqueue_t3(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
+  ConvT3Params p = op.t3p;
+  p.B = B;
+  p.n_mst = cdiv(B, p.S_t);
+  const int CL = op.t3_mode == T3_SINGLE ? 1 : 2;
+  const int items = cdiv(p.n_mst, CL) * p.n_tiles_n;
+  const int grid = CL * std::min(items, h->sm_count / CL);
+  int rc = DAD_ERR_INVALID;
+#define T3_CASE(gw, mh, mode, ns) if (op.GW == gw && op.t3_MH == mh && op.t3_mode == mode && op.t3_NS == ns) rc = launch_t3<gw, mh, mode, ns>(h, op, p, grid, st);
+  T3_FOR_EACH(T3_CASE)
+#undef T3_CASE
+  if (rc == DAD_ERR_INVALID) DAD_FAIL(h, DAD_ERR_INVALID, "internal: no conv_t3 instantiation for GW=%d MH=%d mode=%d NS=%d", op.GW, op.t3_MH, op.t3_mode, op.t3_NS);
+  h->counting += 1;
+  return rc;
+}
+
 template <int BN, int GW>
 int launch_tc(dad_handle *h, const ConvOp &op, const ConvTcParams &p, int grid, cudaStream_t st) {
   auto kern = conv_tc_kernel<BN, GW>;
@@ -407,11 +554,15 @@ int set_kernel_attrs(dad_handle *h) {
   CK(h, (set_tc_attr<32, 0>(h->max_smem_optin)));
   CK(h, (set_tc_attr<64, 0>(h->max_smem_optin)));
   CK(h, (set_tc_attr<128, 0>(h->max_smem_optin)));
+#define T3_ATTR(gw, mh, mode, ns) CK(h, (set_t3_attr<gw, mh, mode, ns>(h->max_smem_optin)));
+  T3_FOR_EACH(T3_ATTR)
+#undef T3_ATTR
   CK(h, cudaFuncSetAttribute(step_project_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   return DAD_OK;
 }
 
 int enqueue_tc(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
+  if (op.t3) return enqueue_t3(h, op, B, st);
   ConvTcParams p = op.tcp;
   p.B = B;
   p.n_tiles_m = cdiv((long long)B * op.g.L_out, TC_BM);
@@ -743,8 +894,13 @@ int dad_create(const dad_config *cfg, dad_handle **out) {
   for (TimeBlock &tb : h->tblocks)
     if ((rc = dev_alloc(h, &tb.tab, (size_t)c.n_timesteps * tb.C))) return fail(rc);
   if (h->bf16)
-    for (ConvOp &op : h->ops)
+    for (ConvOp &op : h->ops) {
       if ((rc = finish_tc_op(h, op))) return fail(rc);
+      if (t3_eligible(h, op) && setup_t3_op(h, op) == DAD_OK) {
+        if ((rc = finish_t3_op(h, op))) return fail(rc);
+        op.t3 = true;
+      }
+    }
   if (cudaDeviceSynchronize() != cudaSuccess) { h->err = "device error during create"; return fail(DAD_ERR_CUDA); }
   *out = h;
   return DAD_OK;
@@ -1148,7 +1304,7 @@ int dad_layer_info(const dad_handle *h, int32_t index, dad_layer_desc *out) {
   out->C_in = op.Cin_real;
   out->C_out = op.g.Cout;
   out->taps = op.g.taps;
-  out->tile_n = op.BN;
+  out->tile_n = op.t3 ? 10000 * op.t3_MH + 1000 * op.t3_mode + 128 * op.t3_NS : op.BN;   /* v3: MH, mode, N per item */
   out->group_width = op.GW;
   out->flops_per_sample = 2LL * op.g.L_out * op.g.taps * op.Cin_real * op.g.Cout;
   return DAD_OK;
@@ -1172,6 +1328,7 @@ int dad_time_layer(dad_handle *h, int32_t index, int32_t B, int32_t iters, float
     CK(h, cudaMalloc(&prof, 4 * sizeof(unsigned long long)));
     CK(h, cudaMemset(prof, 0, 4 * sizeof(unsigned long long)));
     op.tcp.prof = prof;
+    op.t3p.prof = prof;
   }
   h->counting = 0;
   rc = time_launches(h, st, iters, ms, [&]() { return h->bf16 ? enqueue_tc(h, op, B, st) : enqueue_f32(h, op, B, st); });
@@ -1183,6 +1340,7 @@ int dad_time_layer(dad_handle *h, int32_t index, int32_t B, int32_t iters, float
     fprintf(stderr, "[prof] layer %d %s: per warp-tile cycles: wait %.0f  pass1 %.0f  pass2 %.0f  (warp-tiles %llu over %d launches)\n",
             index, op.wname.c_str(), v[0] / n, v[1] / n, v[2] / n, v[3], iters + 1);
     op.tcp.prof = nullptr;
+    op.t3p.prof = nullptr;
     cudaFree(prof);
   }
   return rc;
