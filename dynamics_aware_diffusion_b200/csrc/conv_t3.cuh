@@ -27,7 +27,11 @@ namespace dad {
 constexpr int T3_BN = 128;
 constexpr int T3_BK = 64;
 constexpr int T3_NB = 4;            // weight-tile ring
-constexpr int T3_THREADS = 320;     // producer, MMA issuer, 2 epilogue warpgroups
+#ifndef DAD_T3_NWG
+#define DAD_T3_NWG 3
+#endif
+constexpr int T3_NWG = DAD_T3_NWG;  // epilogue warpgroups; each takes every T3_NWG-th 128-column unit
+constexpr int T3_THREADS = 64 + 128 * T3_NWG;     // producer, MMA issuer, epilogue warpgroups
 constexpr int T3_STAGE_OUT = 128 * T3_BN * 2;          // 32 KB bf16 staging per epilogue warpgroup
 // MODE: how the CTAs of a launch cooperate
 constexpr int T3_SINGLE = 0;        // one CTA per tile, tcgen05 cta_group::1
@@ -66,10 +70,10 @@ __host__ __device__ inline T3Smem t3_smem_layout(int a_stage_bytes, int n_a, int
   s.a_ring = 0;
   s.b_ring = s.a_ring + n_a * a_stage_bytes;
   s.stage_out = s.b_ring + T3_NB * b_stage_bytes;
-  s.bars = s.stage_out + 2 * T3_STAGE_OUT;
+  s.bars = s.stage_out + T3_NWG * T3_STAGE_OUT;
   s.params = s.bars + 256;
   s.scratch = s.params + 20 * cout_pad;                           // 16 B per channel (pairs) + 4 B bias
-  s.total = s.scratch + 2 * 4 * S_t * (ng > 0 ? ng : 1) * 8 + 1024 /*alignment slack*/;
+  s.total = s.scratch + T3_NWG * 4 * S_t * (ng > 0 ? ng : 1) * 8 + 1024 /*alignment slack*/;
   return s;
 }
 
@@ -149,15 +153,18 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   uint64_t *empty_b = bars + 12;           // [T3_NB]
   uint64_t *tfull = bars + 16;             // [ACC]
   uint64_t *tempty = bars + 20;            // [ACC]
-  uint64_t *res_bar = bars + 24;           // [2]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 26);
+  uint64_t *res_bar = bars + 24;           // [T3_NWG] (<= 4)
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 28);
   const uint32_t s_pair = s_base + lay.params;                      // [cout_pad/2] x {g0,g1,b0,b1 | bias0,bias1,t0,t1}
   const uint32_t s_bias = s_pair + 16u * (uint32_t)cout_pad;        // [cout_pad] floats
   const uint32_t s_scr = s_base + lay.scratch;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t cta_rank = 0;
-  if constexpr (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  if constexpr (CL > 1) {
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    cta_rank = __shfl_sync(0xffffffffu, cta_rank, 0);      // tells the compiler the value is warp-uniform
+  }
   const int kch = p.kch1 + p.kch2;
   // persistent schedule: work item -> (group of CL consecutive M super-tiles, N item); the CTAs of a cluster
   // walk the same items in lockstep and take one super-tile of the group each
@@ -181,10 +188,10 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     }
     for (int s = 0; s < ACC; ++s) {
       ptx::mbar_init(&tfull[s], 1);
-      ptx::mbar_init(&tempty[s], MODE == T3_PAIR ? 8 : 4);     // pair: the epilogue warps of both CTAs
+      // every 128-column unit of the item is drained by 4 warps; pair: the epilogue warps of both CTAs
+      ptx::mbar_init(&tempty[s], (MODE == T3_PAIR ? 8 : 4) * NS);
     }
-    ptx::mbar_init(&res_bar[0], 1);
-    ptx::mbar_init(&res_bar[1], 1);
+    for (int s = 0; s < T3_NWG; ++s) ptx::mbar_init(&res_bar[s], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -214,11 +221,15 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   __syncthreads();
   if constexpr (CL > 1) ptx::cluster_sync();      // the peer's barriers exist before anything is signalled at them
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
+  // The producer and MMA warps stay CONVERGED: all 32 lanes walk the loops with warp-uniform values and only
+  // the asynchronous instructions are issued by one elected lane.  (Inside `if (lane == 0)` the compiler has to
+  // assume per-lane operands and wraps every UTMALDG / UTCHMMA in an elect-broadcast loop of ~20 instructions.)
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0 && !(p.debug & 2)) {
+    if (!(p.debug & 2)) {
+      const bool leader_lane = ptx::elect_one();
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       // pair mode: both CTAs' loads complete on the LEADER's full barriers (the MMA issuer lives there)
@@ -234,21 +245,24 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           uint8_t *dst = smem + lay.a_ring + sa * p.a_stage_bytes;
           const CUtensorMap *am = (ch < p.kch1) ? &tmA1 : &tmA2;
           const int c0 = (ch < p.kch1 ? ch : ch - p.kch1) * T3_BK;
-          if (p.debug & 64) {
-            if (MODE != T3_PAIR || cta_rank == 0) ptx::mbar_arrive(&full_a[sa]);   // profiling: MMAs without TMA
-          } else if constexpr (MODE == T3_PAIR) {
-            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_a[sa], 2u * (uint32_t)p.a_tx_bytes);
-            ptx::tma_load_3d_2sm(dst, am, lead_full_a + 8u * sa, c0, b0, -p.halo_lo);
-          } else {
-            ptx::mbar_arrive_expect_tx(&full_a[sa], (uint32_t)p.a_tx_bytes);
-            ptx::tma_load_3d(dst, am, &full_a[sa], c0, b0, -p.halo_lo);
+          if (leader_lane) {
+            if (p.debug & 64) {
+              if (MODE != T3_PAIR || cta_rank == 0) ptx::mbar_arrive(&full_a[sa]);   // profiling: MMAs without TMA
+            } else if constexpr (MODE == T3_PAIR) {
+              if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_a[sa], 2u * (uint32_t)p.a_tx_bytes);
+              ptx::tma_load_3d_2sm(dst, am, lead_full_a + 8u * sa, c0, b0, -p.halo_lo);
+            } else {
+              ptx::mbar_arrive_expect_tx(&full_a[sa], (uint32_t)p.a_tx_bytes);
+              ptx::tma_load_3d(dst, am, &full_a[sa], c0, b0, -p.halo_lo);
+            }
           }
           if (++sa == p.n_a_stages) { sa = 0; pha ^= 1; }
           for (int t = 0; t < p.taps; ++t) {
             ptx::mbar_wait(&empty_b[sb], phb ^ 1);
             uint8_t *wdst = smem + lay.b_ring + sb * p.b_stage_bytes;
             const int k0 = (t * kch + ch) * T3_BK;
-            if (p.debug & 64) {
+            if (!leader_lane) {
+            } else if (p.debug & 64) {
               if (MODE != T3_PAIR || cta_rank == 0) ptx::mbar_arrive(&full_b[sb]);
             } else if constexpr (MODE == T3_SINGLE) {
               ptx::mbar_arrive_expect_tx(&full_b[sb], (uint32_t)p.b_stage_bytes);
@@ -272,7 +286,8 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
     // One thread feeds the tensor core (the pair leader's, in pair mode); descriptors advance by adding constants.
-    if (lane == 0 && (MODE != T3_PAIR || cta_rank == 0)) {
+    if (MODE != T3_PAIR || cta_rank == 0) {
+      const bool leader_lane = ptx::elect_one();
       constexpr uint32_t idesc = ptx::make_idesc_bf16(MODE == T3_PAIR ? 256 : 128, BN_ITEM);
       const uint64_t dconst = ptx::make_smem_desc_sw128(0);
       const uint32_t a_lo0 = ((s_base + lay.a_ring) >> 4), a_lo_step = (uint32_t)p.a_stage_bytes >> 4;
@@ -303,6 +318,7 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               ptx::tc_fence_after();
               const uint64_t db = dconst | (uint64_t)(b_lo0 + sb * b_lo_step);
               const uint32_t acc_kb = (ch | t) != 0;     // the first K block of an item overwrites the accumulator
+              if (leader_lane) {
 #pragma unroll
               for (int h = 0; h < MH; ++h) {
                 // tap t = the same tile viewed tap_row rows further down (a multiple of the 1024 B swizzle atom)
@@ -318,19 +334,27 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               if constexpr (MODE == T3_SINGLE) ptx::umma_commit(&empty_b[sb]);
               else if constexpr (MODE == T3_MCAST) ptx::umma_commit_mc(&empty_b[sb], MC_MASK);
               else ptx::umma_commit_2sm_mc(&empty_b[sb], MC_MASK);
+              }
+              __syncwarp();
               if (++sb == T3_NB) { sb = 0; phb ^= 1; }
               da += tap_step;
             }
-            if constexpr (MODE == T3_PAIR) ptx::umma_commit_2sm_mc(&empty_a[sa], MC_MASK);
-            else ptx::umma_commit(&empty_a[sa]);
+            if (leader_lane) {
+              if constexpr (MODE == T3_PAIR) ptx::umma_commit_2sm_mc(&empty_a[sa], MC_MASK);
+              else ptx::umma_commit(&empty_a[sa]);
+            }
+            __syncwarp();
             if (++sa == n_a) { sa = 0; pha ^= 1; }
           }
         }
+        if (leader_lane) {
 #pragma unroll
-        for (int h = 0; h < MH; ++h) {
-          if constexpr (MODE == T3_PAIR) ptx::umma_commit_2sm_mc(&tfull[(it * MH + h) % ACC], MC_MASK);
-          else ptx::umma_commit(&tfull[(it * MH + h) % ACC]);
+          for (int h = 0; h < MH; ++h) {
+            if constexpr (MODE == T3_PAIR) ptx::umma_commit_2sm_mc(&tfull[(it * MH + h) % ACC], MC_MASK);
+            else ptx::umma_commit(&tfull[(it * MH + h) % ACC]);
+          }
         }
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -373,16 +397,23 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       }
     };
 
-    if (p.has_res && elected && first_item + wg * item_stride < total_items) request_residual(first_item + wg * item_stride, 0, 0);
+    // units: u = it * NS + ns (one 128-column sub-tile of work item `it`, all MH halves); warpgroup wg takes u = wg (mod NWG)
+    if (p.has_res && elected) {
+      const int item0 = first_item + (wg / NS) * item_stride;
+      if (item0 < total_items) request_residual(item0, wg % NS, 0);
+    }
 
-    int it = wg;
-    for (int item = first_item + wg * item_stride; item < total_items; item += 2 * item_stride, it += 2) {
+    for (int u = wg;; u += T3_NWG) {
+      const int it = u / NS, ns = u - it * NS;
+      const int item = first_item + it * item_stride;
+      if (item >= total_items) break;
       if (p.prof) pc_t0 = clock64();
       const int gm = item / n_tiles_n, tn = item - gm * n_tiles_n;
       const int tm = gm * CL + (int)cta_rank;
       const int b0 = tm * p.S_t;
       const bool tile_ok = tm < p.n_mst;
-      const int nitem = item + 2 * item_stride;
+      const int nu = u + T3_NWG, nit = nu / NS, nns = nu - nit * NS;     // this warpgroup's next unit
+      const int nitem = first_item + nit * item_stride;
       uint32_t t_addr[MH];
 #pragma unroll
       for (int h = 0; h < MH; ++h) {
@@ -399,12 +430,11 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll
         for (int h = 0; h < MH; ++h) release_acc((it * MH + h) % ACC);
         ptx::named_bar_sync(1 + wg, 128);
-        if (p.has_res && elected && nitem < total_items) request_residual(nitem, 0, 0);
+        if (p.has_res && elected && nitem < total_items) request_residual(nitem, nns, 0);
         continue;
       }
 
-#pragma unroll 1
-      for (int ns = 0; ns < NS; ++ns) {
+      {
         const int n0 = tn * BN_ITEM + ns * T3_BN;
         const uint32_t col0 = (uint32_t)(ns * T3_BN);
         if constexpr (GW > 0) {
@@ -555,15 +585,15 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             ptx::sts128u(ad0, make_uint4(ow[0], ow[1], ow[2], ow[3]));
             ptx::sts128u(ad1, make_uint4(ow[4], ow[5], ow[6], ow[7]));
           }
-          // accumulator h is drained once its last sub-tile has been read: hand it back to the MMA issuer
-          if (ns == NS - 1) release_acc((it * MH + h) % ACC);
+          // this unit no longer needs accumulator h (the barrier counts all units of the item)
+          release_acc((it * MH + h) % ACC);
           // staged tile -> global with a TMA store (rows of samples >= B land in workspace padding)
           ptx::fence_proxy_async();
           ptx::named_bar_sync(1 + wg, 128);
           // the unit that uses the staging buffer next
           int nx_item = item, nx_ns = ns, nx_h = h + 1;
-          if (nx_h == MH) { nx_h = 0; if (++nx_ns == NS) { nx_ns = 0; nx_item = nitem; } }
-          const bool same_item = nx_item == item;
+          if (nx_h == MH) { nx_h = 0; nx_ns = nns; nx_item = nitem; }
+          const bool same_item = (h + 1 < MH);
           if (elected) {
             if (!(p.debug & 4)) {
               ptx::tma_store_3d(&tmO, stg, n0, b0, h * pos_per_half);
@@ -577,7 +607,7 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           }
           // without a residual: the next pass 2 of this item must not overwrite the buffer while it is being read
           // (across items the wait happens right before the statistics barrier)
-          if (!p.has_res && same_item && MH > 1 && nx_ns == ns) {
+          if (!p.has_res && same_item) {
             if (elected) ptx::bulk_wait_read0();
             ptx::named_bar_sync(1 + wg, 128);
           }
