@@ -71,7 +71,7 @@ __host__ __device__ inline T3Smem t3_smem_layout(int a_stage_bytes, int n_a, int
   s.b_ring = s.a_ring + n_a * a_stage_bytes;
   s.stage_out = s.b_ring + T3_NB * b_stage_bytes;
   s.bars = s.stage_out + T3_NWG * T3_STAGE_OUT;
-  s.params = s.bars + 256;
+  s.params = s.bars + 512;
   s.scratch = s.params + 20 * cout_pad;                           // 16 B per channel (pairs) + 4 B bias
   s.total = s.scratch + T3_NWG * 4 * S_t * (ng > 0 ? ng : 1) * 8 + 1024 /*alignment slack*/;
   return s;
@@ -151,10 +151,14 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   uint64_t *empty_a = bars + 4;            // [4]
   uint64_t *full_b = bars + 8;             // [T3_NB]
   uint64_t *empty_b = bars + 12;           // [T3_NB]
-  uint64_t *tfull = bars + 16;             // [ACC]
-  uint64_t *tempty = bars + 20;            // [ACC]
-  uint64_t *res_bar = bars + 24;           // [T3_NWG] (<= 4)
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 28);
+  uint64_t *tempty = bars + 16;            // [ACC]
+  uint64_t *res_bar = bars + 20;           // [T3_NWG] (<= 4)
+  // "accumulator ready" is signalled PER CONSUMER: unit u (the k-th unit of warpgroup w = u % NWG, k = u / NWG)
+  // completes ufull[w][k & 1].  Every barrier is then waited on in strictly consecutive phases by one warpgroup;
+  // a per-accumulator-stage barrier would be revisited by a warpgroup only every few phases and its parity
+  // test would alias.
+  uint64_t *ufull = bars + 24;             // [T3_NWG][2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 32);
   const uint32_t s_pair = s_base + lay.params;                      // [cout_pad/2] x {g0,g1,b0,b1 | bias0,bias1,t0,t1}
   const uint32_t s_bias = s_pair + 16u * (uint32_t)cout_pad;        // [cout_pad] floats
   const uint32_t s_scr = s_base + lay.scratch;
@@ -186,8 +190,8 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       ptx::mbar_init(&full_b[s], 1);
       ptx::mbar_init(&empty_b[s], MODE == T3_MCAST ? 2 : 1);   // multicast: both CTAs must have consumed the slot
     }
+    for (int s = 0; s < 2 * T3_NWG; ++s) ptx::mbar_init(&ufull[s], 1);
     for (int s = 0; s < ACC; ++s) {
-      ptx::mbar_init(&tfull[s], 1);
       // every 128-column unit of the item is drained by 4 warps; pair: the epilogue warps of both CTAs
       ptx::mbar_init(&tempty[s], (MODE == T3_PAIR ? 8 : 4) * NS);
     }
@@ -349,9 +353,11 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         }
         if (leader_lane) {
 #pragma unroll
-          for (int h = 0; h < MH; ++h) {
-            if constexpr (MODE == T3_PAIR) ptx::umma_commit_2sm_mc(&tfull[(it * MH + h) % ACC], MC_MASK);
-            else ptx::umma_commit(&tfull[(it * MH + h) % ACC]);
+          for (int ns = 0; ns < NS; ++ns) {
+            const int u = it * NS + ns, k = u / T3_NWG;
+            uint64_t *bar = &ufull[(u - k * T3_NWG) * 2 + (k & 1)];
+            if constexpr (MODE == T3_PAIR) ptx::umma_commit_2sm_mc(bar, MC_MASK);
+            else ptx::umma_commit(bar);
           }
         }
         __syncwarp();
@@ -415,13 +421,12 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const int nu = u + T3_NWG, nit = nu / NS, nns = nu - nit * NS;     // this warpgroup's next unit
       const int nitem = first_item + nit * item_stride;
       uint32_t t_addr[MH];
-#pragma unroll
-      for (int h = 0; h < MH; ++h) {
-        const int u = it * MH + h;
-        const int as = u % ACC;
-        ptx::mbar_wait(&tfull[as], (u / ACC) & 1);
-        t_addr[h] = tmem_base + as * BN_ITEM + ((uint32_t)(q * 32) << 16);
+      {
+        const int k = u / T3_NWG;
+        ptx::mbar_wait(&ufull[wg * 2 + (k & 1)], (k >> 1) & 1);
       }
+#pragma unroll
+      for (int h = 0; h < MH; ++h) t_addr[h] = tmem_base + ((it * MH + h) % ACC) * BN_ITEM + ((uint32_t)(q * 32) << 16);
       ptx::tc_fence_after();
       if (p.prof) { pc_t1 = clock64(); pc_wait += pc_t1 - pc_t0; pc_t0 = pc_t1; }
       if ((p.debug & 1) || !tile_ok) {

@@ -73,6 +73,21 @@ def test_projection_idempotent_and_reduces_residual(pointmaze_full):
     assert helpers.rel_l2((fa + fb - fab).cpu().numpy(), f0.cpu().numpy()) < 1e-4
 
 
+def test_large_batch_rows_equal_small_batch_rows(pointmaze_full):
+    """Tile-scheduling regression: a sample's U-Net output must not depend on where it sits in the batch, on how
+    many tiles / CTA pairs / warpgroups the launch uses, nor vary between runs (bitwise)."""
+    dif, pol, P, nz = pointmaze_full
+    g = torch.Generator(device=_dev()).manual_seed(11)
+    x = torch.randn(4096, 32, 6, device=_dev(), generator=g)
+    t = torch.full((4096,), 123, device=_dev(), dtype=torch.long)
+    full = dif.model(x, t)
+    again = dif.model(x, t)
+    assert torch.equal(full, again), "run-to-run variation: a race in the kernels"
+    for lo, n in ((0, 64), (1000, 37), (4032, 64), (2047, 2)):
+        part = dif.model(x[lo:lo + n].contiguous(), t[:n])
+        assert torch.equal(part, full[lo:lo + n]), "rows [%d, %d) depend on the batch they are evaluated in" % (lo, lo + n)
+
+
 def test_chunking_equals_single_pass():
     """B larger than the workspace capacity is processed in chunks with identical results (ragged last chunk)."""
     from dynamics_aware_diffusion_b200 import TemporalUnet, GaussianDiffusion
