@@ -176,6 +176,7 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   const int total_items = n_groups_m * n_tiles_n;
   const int first_item = blockIdx.x / CL, item_stride = gridDim.x / CL;
 
+  ptx::griddep_launch();                          // the next kernel may begin its own set-up
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA1);
     ptx::prefetch_tmap(&tmA2);
@@ -202,6 +203,8 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     if constexpr (MODE == T3_PAIR) { ptx::tmem_alloc_2sm(tmem_slot, 512); ptx::tmem_relinquish_2sm(); }
     else { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
   }
+  // everything above touched no global data; from here on the previous kernels' results are needed
+  ptx::griddep_wait();
   if (warp >= 2) {
     const int step = p.ls->step;
     const float *tt = (p.ttab && !p.ls->t_rows) ? p.ttab + (size_t)step * p.Cout : nullptr;

@@ -111,6 +111,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   const int num_kb = p.taps * kch;
   const int spt = TC_BM / p.L_out;              // samples per M-tile
 
+  ptx::griddep_launch();
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA1);
     ptx::prefetch_tmap(&tmA2);
@@ -129,6 +130,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     ptx::tmem_relinquish();
   }
+  ptx::griddep_wait();                            // no global data was touched above
   if (warp >= 2) {
     // per-column epilogue parameters -> shared memory, once per CTA (all tiles of this CTA reuse them)
     const int step = p.ls->step;

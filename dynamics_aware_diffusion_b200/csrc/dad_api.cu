@@ -139,6 +139,41 @@ int dev_alloc(dad_handle *h, T **p, size_t n) {
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Every kernel of the sampling step is launched with programmatic stream serialization: it may start (and run
+// its set-up) while its predecessor drains, and calls griddepcontrol.wait before touching global data.
+// DAD_PDL=0 disables the attribute (plain stream order).
+inline bool pdl_enabled() {
+  static const bool on = !(getenv("DAD_PDL") && atoi(getenv("DAD_PDL")) == 0);
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
+                     Args &&...args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (cluster > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = (unsigned)cluster;
+    at[n].val.clusterDim.y = 1;
+    at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = (unsigned)n;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 int new_act(dad_handle *h, int L, int C) {
   Act a;
   a.off = h->act_bytes_per_sample;
@@ -488,19 +523,8 @@ cudaError_t set_t3_attr(int max_optin) {
 
 template <int GW, int MH, int MODE, int NS>
 int launch_t3(dad_handle *h, const ConvOp &op, const ConvT3Params &p, int grid, cudaStream_t st) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(T3_THREADS);
-  cfg.dynamicSmemBytes = (size_t)op.t3_smem;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = MODE == T3_SINGLE ? 1 : 2;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_t3_kernel<GW, MH, MODE, NS>, op.t3A1, op.t3A2, op.t3W, op.t3R, op.t3O, p);
+  cudaError_t e = launch_k(conv_t3_kernel<GW, MH, MODE, NS>, dim3((unsigned)grid), dim3(T3_THREADS), (size_t)op.t3_smem, st,
+                           MODE == T3_SINGLE ? 1 : 2, op.t3A1, op.t3A2, op.t3W, op.t3R, op.t3O, p);
   if (e != cudaSuccess) DAD_FAIL(h, DAD_ERR_CUDA, "conv_t3 launch failed: %s", cudaGetErrorString(e));
   return DAD_OK;
 }
@@ -527,7 +551,7 @@ int enqueue_t3(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
 template <int BN, int GW>
 int launch_tc(dad_handle *h, const ConvOp &op, const ConvTcParams &p, int grid, cudaStream_t st) {
   auto kern = conv_tc_kernel<BN, GW>;
-  kern<<<grid, TC_THREADS, TcCfg<BN>::smem_bytes(op.Cout_pad), st>>>(op.tmA1, op.tmA2, op.tmW, p);
+  launch_k(kern, dim3((unsigned)grid), dim3(TC_THREADS), (size_t)TcCfg<BN>::smem_bytes(op.Cout_pad), st, 1, op.tmA1, op.tmA2, op.tmW, p);
   return DAD_OK;
 }
 
@@ -593,8 +617,8 @@ int enqueue_f32(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
   p.B = B;
   const bool vec = (op.g.C1 % 4 == 0) && (op.g.C2 % 4 == 0) && (op.g.Cout % 4 == 0);
   dim3 grid(cdiv((long long)B * op.g.L_out, F32_BM), cdiv(op.g.Cout, F32_BN));
-  if (vec) conv_f32_kernel<EPI_BIAS, true><<<grid, 256, 0, st>>>(p);
-  else conv_f32_kernel<EPI_BIAS, false><<<grid, 256, 0, st>>>(p);
+  if (vec) launch_k(conv_f32_kernel<EPI_BIAS, true>, grid, dim3(256), 0, st, 1, p);
+  else launch_k(conv_f32_kernel<EPI_BIAS, false>, grid, dim3(256), 0, st, 1, p);
   h->counting += 1;
   if (gn) {
     GnF32Params q{};
@@ -607,24 +631,24 @@ int enqueue_f32(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
     q.ls = h->d_ls;
     q.L = op.g.L_out;
     q.C = op.g.Cout;
-    gn_mish_f32_kernel<<<dim3(B, kGroups), 128, 0, st>>>(q);
+    launch_k(gn_mish_f32_kernel, dim3(B, kGroups), dim3(128), 0, st, 1, q);
     h->counting += 1;
   }
   return DAD_OK;
 }
 
 // One U-Net forward of the staged trajectories -> d_eps.  (TemporalUnet.forward, temporal_unet.py:199-241)
-int enqueue_unet(dad_handle *h, int B, cudaStream_t st) {
+int enqueue_unet(dad_handle *h, int B, cudaStream_t st, bool advance = false) {
   const dad_config &c = h->cfg;
   const size_t rows = (size_t)B * c.horizon;
   if (h->bf16) {
-    const size_t n = rows * h->Cpad_in;
-    stage_x_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->d_ls, nullptr, reinterpret_cast<__nv_bfloat16 *>(act_ptr(h, 0)), rows,
-                                                 c.transition_dim, h->Cpad_in);
+    const size_t n = rows * (h->Cpad_in / 8);
+    launch_k(stage_x_kernel, dim3(cdiv(n, 256)), dim3(256), 0, st, 1, h->d_ls, (float *)nullptr,
+             reinterpret_cast<__nv_bfloat16 *>(act_ptr(h, 0)), rows, c.transition_dim, h->Cpad_in, advance ? 1 : 0);
   } else {
     const size_t n = rows * c.transition_dim;
-    stage_x_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->d_ls, reinterpret_cast<float *>(act_ptr(h, 0)), nullptr, rows,
-                                                 c.transition_dim, 0);
+    launch_k(stage_x_kernel, dim3(cdiv(n, 256)), dim3(256), 0, st, 1, h->d_ls, reinterpret_cast<float *>(act_ptr(h, 0)),
+             (__nv_bfloat16 *)nullptr, rows, c.transition_dim, 0, advance ? 1 : 0);
   }
   h->counting += 1;
   for (const ConvOp &op : h->ops) {
@@ -660,20 +684,20 @@ int enqueue_step(dad_handle *h, const float *model_out, int B, bool project, boo
   if (!project) {
     p.to_tmp = 0;
     const int grid = (int)std::min<size_t>(cdiv(total4, 256), (size_t)h->sm_count * 8);
-    step_pointwise_kernel<<<grid, 256, 0, st>>>(p);
+    launch_k(step_pointwise_kernel, dim3(grid), dim3(256), 0, st, 1, p);
     h->counting += 1;
   } else {
     const size_t fused_smem = ((size_t)h->D * h->D + (size_t)h->D * STEP_SB + h->D) * sizeof(float);
     if (fused_smem <= (size_t)h->max_smem_optin) {
       const int grid = std::min(cdiv(B, STEP_SB), h->sm_count);
-      step_project_fused_kernel<<<grid, 256, fused_smem, st>>>(p);
+      launch_k(step_project_fused_kernel, dim3(grid), dim3(256), fused_smem, st, 1, p);
       h->counting += 1;
     } else {
       // large D: pointwise part to scratch, then the projector as a tiled GEMM whose epilogue
       // blends, inpaints and writes x (K8).
       p.to_tmp = 1;
       const int grid = (int)std::min<size_t>(cdiv(total4, 256), (size_t)h->sm_count * 8);
-      step_pointwise_kernel<<<grid, 256, 0, st>>>(p);
+      launch_k(step_pointwise_kernel, dim3(grid), dim3(256), 0, st, 1, p);
       ConvF32Params g{};
       g.in1 = h->d_xtmp;
       g.w = h->d_Nt;            // Nt[k][d] is exactly the [c][n] weight layout
@@ -686,14 +710,11 @@ int enqueue_step(dad_handle *h, const float *model_out, int B, bool project, boo
       g.cond_vals = h->d_cond;
       g.T = c.transition_dim;
       dim3 grid2(cdiv(B, F32_BM), cdiv(h->D, F32_BN));
-      conv_f32_kernel<EPI_PROJECT, true><<<grid2, 256, 0, st>>>(g);
+      launch_k(conv_f32_kernel<EPI_PROJECT, true>, grid2, dim3(256), 0, st, 1, g);
       h->counting += 2;
     }
   }
-  if (advance) {
-    advance_step_kernel<<<1, 1, 0, st>>>(h->d_ls);
-    h->counting += 1;
-  }
+  (void)advance;    // the step index is advanced by the first kernel of the captured step (stage_x_kernel)
   CK(h, cudaGetLastError());
   return DAD_OK;
 }
@@ -726,8 +747,9 @@ int get_graph(dad_handle *h, int B, bool project, GraphEntry **out) {
   cudaGraph_t graph = nullptr;
   h->counting = 0;
   CK(h, cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
-  int rc = enqueue_unet(h, B, h->cap_stream);
-  if (!rc) rc = enqueue_step(h, h->d_eps, B, project, true, h->cap_stream);
+  // captured step: [stage x, step index -= 1] -> U-Net -> fused step kernel; the loop starts one index high
+  int rc = enqueue_unet(h, B, h->cap_stream, true);
+  if (!rc) rc = enqueue_step(h, h->d_eps, B, project, false, h->cap_stream);
   cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
   if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
   if (e != cudaSuccess) DAD_FAIL(h, DAD_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
@@ -1179,7 +1201,7 @@ int dad_sample(dad_handle *h, float *x, const float *noise_seq, uint64_t seed, u
   for (int c0 = 0; c0 < B; c0 += h->cfg.max_batch) {
     const int Bc = std::min(h->cfg.max_batch, B - c0);
     LoopState ls{};
-    ls.step = n_steps - 1;
+    ls.step = n_steps;          // every graph replay first decrements it
     ls.n_steps = n_steps;
     ls.flags = flags;
     ls.x = x + (size_t)c0 * D;
@@ -1240,7 +1262,7 @@ int dad_get_info(const dad_handle *h, dad_info *out) {
   out->conv_flops_per_sample = h->conv_flops;
   long long per_step = 1;  // stage_x
   for (const ConvOp &op : h->ops) per_step += (h->bf16 || op.gname.empty()) ? 1 : 2;
-  per_step += 2;           // fused step kernel + advance (projector GEMM adds one for large D)
+  per_step += 1;           // fused step kernel (the projector GEMM adds one for large D)
   out->launches_per_step = per_step;
   out->workspace_bytes = (int64_t)(h->act_bytes_per_sample * (size_t)h->cfg.max_batch);
   out->n_conv_layers = (int32_t)h->ops.size();
@@ -1261,7 +1283,7 @@ int dad_sample_profile(dad_handle *h, float *x, uint64_t seed, uint64_t sample_o
   CK(h, cudaSetDevice(h->cfg.device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   LoopState ls{};
-  ls.step = n_steps - 1;
+  ls.step = n_steps;            // every graph replay first decrements it
   ls.n_steps = n_steps;
   ls.flags = flags;
   ls.x = x;

@@ -2,6 +2,7 @@
 // weight re-packers.  Everything is channels-last: activations (B, L, C).
 #pragma once
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace dad {
 
@@ -34,6 +35,8 @@ template <int EPI, bool VEC>
 __global__ void __launch_bounds__(256) conv_f32_kernel(const ConvF32Params p) {
   __shared__ float As[F32_BK][F32_BM + 4];
   __shared__ float Bs[F32_BK][F32_BN];
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   const ConvGeom &g = p.g;
   const int Cin = g.C1 + g.C2;
   const int K = g.taps * Cin;
@@ -173,6 +176,8 @@ struct GnF32Params {
 
 __global__ void __launch_bounds__(128) gn_mish_f32_kernel(const GnF32Params p) {
   __shared__ float red[32];
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   const int b = blockIdx.x, grp = blockIdx.y;
   const int gw = p.C / kGroups;
   const int n = p.L * gw;

@@ -10,6 +10,7 @@
 // projector in shared memory and reduces with warp shuffles.
 #pragma once
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace dad {
 
@@ -131,6 +132,8 @@ __device__ __forceinline__ float cond_override(const LoopState &ls, const float 
 
 // Variant A: no projector in this kernel (guided / plain policies, or a projector GEMM follows).
 __global__ void __launch_bounds__(256) step_pointwise_kernel(const StepParams p) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   const LoopState ls = *p.ls;
   const int i = ls.step;
   const float cr = p.sqrt_recip[i], crm1 = p.sqrt_recipm1[i], c1 = p.coef1[i], c2 = p.coef2[i];
@@ -173,6 +176,12 @@ __global__ void __launch_bounds__(256) step_project_fused_kernel(const StepParam
   float *Nt = smem;                 // D * D
   float *xs = Nt + (size_t)D * D;   // D * STEP_SB, layout xs[k][s]
   float *qs = xs + (size_t)D * STEP_SB;
+  ptx::griddep_launch();
+  // the projector itself is constant: stage it while the U-Net's last kernel drains
+  for (int idx = threadIdx.x * 4; idx < D * D; idx += blockDim.x * 4)
+    *reinterpret_cast<float4 *>(Nt + idx) = __ldg(reinterpret_cast<const float4 *>(p.Nt + idx));
+  for (int d = threadIdx.x; d < D; d += blockDim.x) qs[d] = p.q[d];
+  ptx::griddep_wait();
   const LoopState ls = *p.ls;
   const int i = ls.step;
   const float cr = p.sqrt_recip[i], crm1 = p.sqrt_recipm1[i], c1 = p.coef1[i], c2 = p.coef2[i];
@@ -183,10 +192,6 @@ __global__ void __launch_bounds__(256) step_project_fused_kernel(const StepParam
   const bool inpaint_first = (ls.flags & 4u) != 0;
   const int n_cond = (ls.flags & 1u) ? ls.n_cond : 0;
   float *tr = ls.trace ? ls.trace + (size_t)(ls.n_steps - 1 - i) * ls.trace_stride : nullptr;
-
-  for (int idx = threadIdx.x * 4; idx < D * D; idx += blockDim.x * 4)
-    *reinterpret_cast<float4 *>(Nt + idx) = __ldg(reinterpret_cast<const float4 *>(p.Nt + idx));
-  for (int d = threadIdx.x; d < D; d += blockDim.x) qs[d] = p.q[d];
 
   const int n_groups = (p.B + STEP_SB - 1) / STEP_SB;
   const int D4 = D / 4;
@@ -243,19 +248,32 @@ __global__ void __launch_bounds__(256) step_project_fused_kernel(const StepParam
 
 // ---- loop-state plumbing ------------------------------------------------------------------
 __global__ void set_loop_state_kernel(LoopState *dst, const LoopState v) { *dst = v; }
-__global__ void advance_step_kernel(LoopState *ls) { ls->step -= 1; }
 
 // Stage the current trajectories as the U-Net's first operand (fixed address -> graph-replayable):
-// fp32 copy (fp32 mode) or bf16 with zero-padded channels (bf16 mode).
-__global__ void __launch_bounds__(256) stage_x_kernel(const LoopState *lsp, float *out_f32,
-                                                       __nv_bfloat16 *out_bf16, size_t rows, int T, int Cpad) {
+// fp32 copy (fp32 mode) or bf16 with zero-padded channels (bf16 mode; 8 channels = one 16-byte store per thread).
+// With `advance` the kernel also moves the loop to its next step index: it is the FIRST kernel of the captured
+// step, does not read the index itself, and every later kernel of the step sees the new value.
+__global__ void __launch_bounds__(256) stage_x_kernel(LoopState *lsp, float *out_f32, __nv_bfloat16 *out_bf16,
+                                                       size_t rows, int T, int Cpad, int advance) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   const float *x = lsp->x;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (advance && idx == 0) lsp->step -= 1;
   if (out_bf16) {
-    if (idx >= rows * (size_t)Cpad) return;
-    const size_t r = idx / Cpad;
-    const int c = (int)(idx - r * Cpad);
-    out_bf16[idx] = __float2bfloat16_rn(c < T ? x[r * T + c] : 0.f);
+    const int vec = Cpad >> 3;
+    if (idx >= rows * (size_t)vec) return;
+    const size_t r = idx / vec;
+    const int c0 = (int)(idx - r * vec) << 3;
+    uint4 o;
+    __nv_bfloat162 *o2 = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + 2 * j;
+      const float a = c < T ? x[r * T + c] : 0.f, b = c + 1 < T ? x[r * T + c + 1] : 0.f;
+      o2[j] = __floats2bfloat162_rn(a, b);
+    }
+    *reinterpret_cast<uint4 *>(out_bf16 + r * Cpad + c0) = o;
   } else {
     if (idx >= rows * (size_t)T) return;
     out_f32[idx] = x[idx];
