@@ -207,7 +207,7 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   ptx::griddep_wait();
   if (warp >= 2) {
     const int step = p.ls->step;
-    const float *tt = (p.ttab && !p.ls->t_rows) ? p.ttab + (size_t)step * p.Cout : nullptr;
+    const float *tt = p.ttab ? p.ttab + (size_t)step * p.Cout : nullptr;     // uniform timestep only (host guarantees)
     for (int n = threadIdx.x - 64; n < cout_pad; n += T3_THREADS - 64) {
       const bool in = n < p.Cout;
       float g = 0.f, e = 0.f;
@@ -381,8 +381,6 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     const uint32_t scr = s_scr + (uint32_t)wg * (4u * p.S_t * NG * 8u);      // [4 warps][S_t][NG] x (sum, sumsq)
     const uint32_t row_off = (uint32_t)r * 128u;
     const uint32_t swz = (uint32_t)(r & 7);
-    const bool rows_t = (p.ttab != nullptr) && (p.ls->t_rows != nullptr);
-    const long long *t_rows = rows_t ? p.ls->t_rows : nullptr;
     const uint32_t tempty0 = (MODE == T3_PAIR) ? ptx::mapa(ptx::smem_u32(&tempty[0]), 0) : ptx::smem_u32(&tempty[0]);
     uint32_t res_phase = 0;
     long long pc_wait = 0, pc_p1 = 0, pc_p2 = 0, pc_n = 0, pc_t0 = 0, pc_t1 = 0;
@@ -507,11 +505,9 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll 1
         for (int h = 0; h < MH; ++h) {
           if (p.has_res) { ptx::mbar_wait(&res_bar[wg], res_phase); res_phase ^= 1; }
-          const float *trow = nullptr;
-          if (rows_t) {
-            const int b = b0 + s_smp;
-            trow = p.ttab + (size_t)(b < p.B ? t_rows[b] : 0) * p.Cout + n0;
-          }
+          f32x2 rg2[GPC], nm2[GPC];      // (rstd, -mean) of the current group(s), carried across the chunks of a wide group
+#pragma unroll
+          for (int g = 0; g < GPC; ++g) { rg2[g] = pk2(0.f, 0.f); nm2[g] = pk2(0.f, 0.f); }
 #pragma unroll 1
           for (int c = 0; c < NCHUNK; ++c) {
             uint32_t v[32];
@@ -520,8 +516,8 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             const uint32_t sp = s_pair + (uint32_t)(nc >> 1) * 32u;
             f32x2 y[CW / 2];
             if constexpr (GW > 0) {
-              f32x2 rg2[GPC], nm2[GPC];
               const int g0 = (GW >= CW) ? c / CPG : c * GPC;
+              if (GW < CW || c % CPG == 0) {
 #pragma unroll
               for (int g = 0; g < GPC; ++g) {
                 float t1 = 0.f, t2 = 0.f;
@@ -536,6 +532,7 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                 const float rs = rsqrtf(var + kGnEps);
                 rg2[g] = pk2(rs, rs);
                 nm2[g] = pk2(-m, -m);
+              }
               }
               f32x2 a2[CW / 2], bsh[CW / 2], tt2[CW / 2];
 #pragma unroll
@@ -552,13 +549,6 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               for (int j = 0; j < CW / 2; ++j) {
                 const f32x2 xn = ffma2(pk2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), a2[j], bsh[j]);
                 y[j] = fadd2((p.debug & 32) ? xn : mish2(xn), tt2[j]);
-              }
-              if (trow) {
-#pragma unroll
-                for (int j = 0; j < CW / 2; ++j) {
-                  const float2 r2 = __ldg(reinterpret_cast<const float2 *>(trow + c * CW + 2 * j));
-                  y[j] = fadd2(y[j], pk2(r2.x, r2.y));
-                }
               }
             } else {
               f32x2 bb[CW / 2];

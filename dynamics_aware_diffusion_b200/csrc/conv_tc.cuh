@@ -53,6 +53,11 @@ struct ConvTcParams {
   int taps;
   int tap_j[kMaxTaps], tap_p[kMaxTaps];
   int out_f32;
+  // projector epilogue (K8): out = x' + alpha[step] * (acc + bias), then inpainting / trace, written to ls->x
+  const float *proj_x;           // x' fp32 (B, D), or nullptr for a plain convolution
+  const float *alpha_tab;
+  const float *cond_vals;
+  int T;
   unsigned long long *prof;      // optional cycle counters (DAD_TC_PROF): [wait, pass1, pass2, tiles] summed over epilogue warps
   int debug;                     // 0 normal; 1 = skip the epilogue arithmetic; 2 = skip TMA + MMA (profiling only, DAD_TC_DEBUG)
 };
@@ -381,7 +386,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           for (int j = 0; j < CW; ++j) y[j] = __uint_as_float(v[j]) + bb[j];
         }
         if (valid && (!(p.debug & 4) || y[0] == 123.456f)) {
-          if (p.out_f32) {
+          if (p.proj_x) {
+            // dynamics projector: y = x' + alpha (N x' + q), Diffuser-style inpainting, optional trace (policies.py:409-485,61-62)
+            const LoopState &ls = *p.ls;
+            const float alpha = p.alpha_tab[ls.step];
+            const int n_cond = ((ls.flags & 1u) && !(ls.flags & 4u)) ? ls.n_cond : 0;
+            const float *xr = p.proj_x + orow + c * CW;
+            float *o = ls.x + orow + c * CW;
+            float *tr = ls.trace ? ls.trace + (size_t)(ls.n_steps - 1 - ls.step) * ls.trace_stride + orow + c * CW : nullptr;
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+              const int n = nc + j;
+              if (n < p.Cout) {
+                float v = xr[j] + alpha * y[j];
+                const int hh = n / p.T, tt = n - hh * p.T;
+                for (int cc = 0; cc < n_cond; ++cc)
+                  if (ls.cond_h[cc] == hh)
+                    v = p.cond_vals[((size_t)cc * (ls.cond_per_batch ? ls.cond_B : 1) +
+                                     (ls.cond_per_batch ? (ls.cond_row0 + b) : 0)) * p.T + tt];
+                o[j] = v;
+                if (tr) tr[j] = v;
+              }
+            }
+          } else if (p.out_f32) {
             float *o = reinterpret_cast<float *>(p.out) + orow + c * CW;
 #pragma unroll
             for (int j = 0; j < CW; ++j)

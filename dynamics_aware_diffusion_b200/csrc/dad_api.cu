@@ -91,9 +91,16 @@ struct dad_handle {
   LoopState *d_ls = nullptr;
   float *d_sched[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   bool have_weights = false, have_sched = false;
+  bool rows_t = false;               // the forward being enqueued has per-row timesteps
   // projector
   float *d_Nt = nullptr, *d_Nrow = nullptr, *d_q = nullptr, *d_alpha = nullptr;
   int projD = 0;
+  // tensor-core projector (bf16 engines): 3-term bf16 split GEMM through conv_tc_kernel<128,0>
+  __nv_bfloat16 *d_projW = nullptr, *d_split = nullptr;
+  float *d_qpad = nullptr;
+  int projKp = 0, projNp = 0;
+  CUtensorMap tmProjA, tmProjW;
+  bool proj_tc = false;
   // conditions
   int n_cond = 0, cond_per_batch = 0, cond_B = 0;
   int cond_h[kMaxCond] = {0};
@@ -586,7 +593,7 @@ int set_kernel_attrs(dad_handle *h) {
 }
 
 int enqueue_tc(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
-  if (op.t3) return enqueue_t3(h, op, B, st);
+  if (op.t3 && !h->rows_t) return enqueue_t3(h, op, B, st);      // conv_t3 assumes one timestep for the whole batch
   ConvTcParams p = op.tcp;
   p.B = B;
   p.n_tiles_m = cdiv((long long)B * op.g.L_out, TC_BM);
@@ -686,6 +693,36 @@ int enqueue_step(dad_handle *h, const float *model_out, int B, bool project, boo
     const int grid = (int)std::min<size_t>(cdiv(total4, 256), (size_t)h->sm_count * 8);
     launch_k(step_pointwise_kernel, dim3(grid), dim3(256), 0, st, 1, p);
     h->counting += 1;
+  } else if (h->proj_tc && ((size_t)h->D * h->D + (size_t)h->D * STEP_SB + h->D) * sizeof(float) > (size_t)h->max_smem_optin) {
+    // large D (the projector does not fit shared memory): pointwise part -> x' (fp32) + its bf16 (hi | lo | hi) split; then one tcgen05 GEMM against (N_hi | N_hi | N_lo)
+    // whose epilogue blends, inpaints and writes x (K8)
+    p.to_tmp = 1;
+    p.split = h->d_split;
+    p.Kp = h->projKp;
+    const int grid = (int)std::min<size_t>(cdiv(total4, 256), (size_t)h->sm_count * 8);
+    launch_k(step_pointwise_kernel, dim3(grid), dim3(256), 0, st, 1, p);
+    ConvTcParams t{};
+    t.bias = h->d_qpad;
+    t.ls = h->d_ls;
+    t.B = B;
+    t.L_out = 1;
+    t.out_mul = 1;
+    t.out_phase = 0;
+    t.Cout = h->D;
+    t.n_tiles_m = cdiv(B, TC_BM);
+    t.n_tiles_n = h->projNp / 128;
+    t.kch1 = 3 * h->projKp / TC_BK;
+    t.kch2 = 0;
+    t.taps = 1;
+    t.out_f32 = 1;
+    t.proj_x = h->d_xtmp;
+    t.alpha_tab = h->d_alpha;
+    t.cond_vals = h->d_cond;
+    t.T = c.transition_dim;
+    const int tiles = t.n_tiles_m * t.n_tiles_n;
+    launch_k(conv_tc_kernel<128, 0>, dim3((unsigned)std::min(tiles, h->sm_count)), dim3(TC_THREADS),
+             (size_t)TcCfg<128>::smem_bytes(h->projNp), st, 1, h->tmProjA, h->tmProjA, h->tmProjW, t);
+    h->counting += 2;
   } else {
     const size_t fused_smem = ((size_t)h->D * h->D + (size_t)h->D * STEP_SB + h->D) * sizeof(float);
     if (fused_smem <= (size_t)h->max_smem_optin) {
@@ -1063,6 +1100,35 @@ int dad_set_projector(dad_handle *h, const float *Nmat, const float *q, const fl
   pack_w_f32_kernel<<<cdiv((long long)D * D, 256), 256, 0, h->own_stream>>>(h->d_Nrow, h->d_Nt, D, D, 1, 1, sel, 0);
   CK(h, cudaStreamSynchronize(h->own_stream));
   h->projD = D;
+  h->proj_tc = false;
+  if (h->bf16 && !(getenv("DAD_PROJ_TC") && atoi(getenv("DAD_PROJ_TC")) == 0)) {
+    const int Kp = (D + 63) / 64 * 64, Np = (D + 127) / 128 * 128;
+    if (!h->d_projW) {
+      int rc;
+      if ((rc = dev_alloc(h, &h->d_projW, (size_t)Np * 3 * Kp))) return rc;
+      if ((rc = dev_alloc(h, &h->d_split, (size_t)h->cfg.max_batch * 3 * Kp))) return rc;
+      if ((rc = dev_alloc(h, &h->d_qpad, (size_t)Np))) return rc;
+      CK(h, cudaMemset(h->d_split, 0, sizeof(__nv_bfloat16) * (size_t)h->cfg.max_batch * 3 * Kp));
+      h->projKp = Kp;
+      h->projNp = Np;
+      // A: (3Kp, 1, 1, max_batch) boxes of 64 x 128 rows; W: (3Kp, Np) boxes of 64 x 128
+      cuuint64_t ad[4] = {(cuuint64_t)3 * Kp, 1, 1, (cuuint64_t)h->cfg.max_batch};
+      cuuint64_t as[3] = {(cuuint64_t)3 * Kp * 2, (cuuint64_t)3 * Kp * 2, (cuuint64_t)3 * Kp * 2};
+      cuuint32_t ab[4] = {64, 1, 1, 128};
+      int rc2 = make_tmap(h, &h->tmProjA, h->d_split, 4, ad, as, ab);
+      if (rc2) return rc2;
+      cuuint64_t wd[2] = {(cuuint64_t)3 * Kp, (cuuint64_t)Np};
+      cuuint64_t ws[1] = {(cuuint64_t)3 * Kp * 2};
+      cuuint32_t wb[2] = {64, 128};
+      if ((rc2 = make_tmap(h, &h->tmProjW, h->d_projW, 2, wd, ws, wb))) return rc2;
+    }
+    CK(h, cudaMemset(h->d_qpad, 0, sizeof(float) * h->projNp));
+    CK(h, cudaMemcpy(h->d_qpad, h->d_q, sizeof(float) * D, cudaMemcpyDeviceToDevice));
+    pack_projector_bf16_kernel<<<cdiv((long long)h->projNp * h->projKp, 256), 256, 0, h->own_stream>>>(
+        h->d_Nrow, h->d_projW, D, h->projKp, h->projNp);
+    CK(h, cudaStreamSynchronize(h->own_stream));
+    h->proj_tc = true;
+  }
   return DAD_OK;
 }
 
@@ -1109,7 +1175,10 @@ int dad_unet_forward(dad_handle *h, const float *x, const int64_t *t, int32_t st
     int rc = set_loop_state(h, ls, st);
     if (rc) return rc;
     h->counting = 0;
-    if ((rc = enqueue_unet(h, Bc, st))) return rc;
+    h->rows_t = t != nullptr;
+    rc = enqueue_unet(h, Bc, st);
+    h->rows_t = false;
+    if (rc) return rc;
     h->launches += h->counting;
     CK(h, cudaMemcpyAsync(eps + (size_t)c0 * h->D, h->d_eps, sizeof(float) * (size_t)Bc * h->D, cudaMemcpyDeviceToDevice, st));
   }

@@ -279,6 +279,22 @@ __global__ void pack_w_bf16_kernel(const float *__restrict__ w, __nv_bfloat16 *_
   out[idx] = __float2bfloat16_rn(v);
 }
 
+// Projector N (D x D fp32, row-major: y_n = sum_k N[n][k] x_k) -> bf16 K-major rows for the 3-term split GEMM:
+// out[n][0:Kp) = hi(N[n][:]), out[n][Kp:2Kp) = hi(N[n][:]), out[n][2Kp:3Kp) = lo(N[n][:]); zero padded to (Np, 3 Kp).
+__global__ void pack_projector_bf16_kernel(const float *__restrict__ Nm, __nv_bfloat16 *__restrict__ out, int D, int Kp,
+                                           int Np) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)Np * Kp) return;
+  const int n = (int)(idx / Kp), k = (int)(idx - (size_t)n * Kp);
+  float v = (n < D && k < D) ? Nm[(size_t)n * D + k] : 0.f;
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  __nv_bfloat16 *row = out + (size_t)n * 3 * Kp;
+  row[k] = hi;
+  row[Kp + k] = hi;
+  row[2 * Kp + k] = lo;
+}
+
 // x fp32 (B, H, T) -> bf16 (B, H, Cpad), zero padded channels: first-layer operand of the bf16 path.
 __global__ void pack_x_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ out, size_t rows,
                                    int T, int Cpad) {

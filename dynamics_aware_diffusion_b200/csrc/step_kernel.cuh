@@ -26,6 +26,8 @@ struct StepParams {
   int B, D, T;
   int predict_epsilon, clip_denoised;
   int to_tmp;                   // 1: write x' to xtmp and skip inpainting (projector GEMM follows)
+  __nv_bfloat16 *split;         // tensor-core projector operand [B][3*Kp]: (hi | lo | hi) bf16 split of x', or nullptr
+  int Kp;
 };
 
 // ---- Philox4x32-10 (Salmon et al. 2011), counter-based: (quad index, step index, sample lo, sample hi)
@@ -159,6 +161,20 @@ __global__ void __launch_bounds__(256) step_pointwise_kernel(const StepParams p)
     const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
     *reinterpret_cast<float4 *>(dst + e) = o4;
     if (tr) *reinterpret_cast<float4 *>(tr + e) = o4;
+    if (p.split) {
+      // x' = hi + lo with hi, lo in bf16: three bf16 products recover fp32-level accuracy on the tensor cores
+      __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        hi[j] = __float2bfloat16_rn(o[j]);
+        lo[j] = __float2bfloat16_rn(o[j] - __bfloat162float(hi[j]));
+      }
+      __nv_bfloat16 *row = p.split + (size_t)b * 3 * p.Kp + d0;
+      const uint2 h2 = *reinterpret_cast<const uint2 *>(hi), l2 = *reinterpret_cast<const uint2 *>(lo);
+      *reinterpret_cast<uint2 *>(row) = h2;
+      *reinterpret_cast<uint2 *>(row + p.Kp) = l2;
+      *reinterpret_cast<uint2 *>(row + 2 * p.Kp) = h2;
+    }
   }
 }
 
