@@ -57,6 +57,7 @@ struct ConvT3Params {
   int n_a_stages;            // 2..4
   int b_stage_bytes;         // bytes of weight tile each CTA keeps per K block
   int has_res;
+  int split_tail;            // 256-wide items: split the partial last round into 128-wide half entries
   int debug;
 };
 
@@ -127,8 +128,8 @@ __device__ __forceinline__ f32x2 mish2(f32x2 y) {
 template <int GW, int MH, int MODE, int NS>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmR,
-               const __grid_constant__ CUtensorMap tmO, const ConvT3Params p) {
+               const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmW2,
+               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO, const ConvT3Params p) {
   static_assert(NS == 1 || (MODE == T3_PAIR && MH == 1), "256-wide items need the CTA pair and one accumulator half");
   constexpr int CL = (MODE == T3_SINGLE) ? 1 : 2;
   constexpr int BN_ITEM = NS * T3_BN;                     // output channels per work item
@@ -175,12 +176,32 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   const int n_groups_m = (p.n_mst + CL - 1) / CL;
   const int total_items = n_groups_m * n_tiles_n;
   const int first_item = blockIdx.x / CL, item_stride = gridDim.x / CL;
+  // Entry j of this CTA (cluster): rounds j < full_rounds take whole items; with 256-wide items the remaining
+  // items (a partial last round) are split into 128-wide HALF entries so that every cluster stays busy.
+  const int full_rounds = (NS == 2 && p.split_tail) ? total_items / item_stride : (1 << 28);
+  const int items_full = (NS == 2 && p.split_tail) ? full_rounds * item_stride : total_items;
+  const int n_half = 2 * (total_items - items_full);
+  auto entry = [&](int j, int &item, bool &half, int &ns_only) -> bool {
+    half = false;
+    ns_only = 0;
+    if (j < full_rounds) {
+      item = first_item + j * item_stride;
+      return item < total_items;
+    }
+    const int g = (j - full_rounds) * item_stride + first_item;
+    if (g >= n_half) return false;
+    item = items_full + (g >> 1);
+    half = true;
+    ns_only = g & 1;
+    return true;
+  };
 
   ptx::griddep_launch();                          // the next kernel may begin its own set-up
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA1);
     ptx::prefetch_tmap(&tmA2);
     ptx::prefetch_tmap(&tmW);
+    ptx::prefetch_tmap(&tmW2);
     ptx::prefetch_tmap(&tmR);
     ptx::prefetch_tmap(&tmO);
     for (int s = 0; s < 4; ++s) {
@@ -242,10 +263,13 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       // pair mode: both CTAs' loads complete on the LEADER's full barriers (the MMA issuer lives there)
       const uint32_t lead_full_a = (MODE == T3_PAIR) ? ptx::mapa(ptx::smem_u32(&full_a[0]), 0) : 0;
       const uint32_t lead_full_b = (MODE == T3_PAIR) ? ptx::mapa(ptx::smem_u32(&full_b[0]), 0) : 0;
-      for (int item = first_item; item < total_items; item += item_stride) {
+      for (int j = 0;; ++j) {
+        int item, ns_only;
+        bool half;
+        if (!entry(j, item, half, ns_only)) break;
         const int gm = item / n_tiles_n, tn = item - gm * n_tiles_n;
         const int tm = gm * CL + (int)cta_rank;
-        const int b0 = tm * p.S_t, n0 = tn * BN_ITEM;
+        const int b0 = tm * p.S_t, n0 = tn * BN_ITEM + ns_only * T3_BN;
         for (int ch = 0; ch < kch; ++ch) {
           // one haloed activation box per 64-channel block, shared by all taps
           ptx::mbar_wait(&empty_a[sa], pha ^ 1);
@@ -279,6 +303,10 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               ptx::mbar_arrive_expect_tx(&full_b[sb], (uint32_t)p.b_stage_bytes);
               ptx::tma_load_2d_mc(wdst + cta_rank * (p.b_stage_bytes / 2), &tmW, &full_b[sb], k0,
                                   n0 + (int)cta_rank * (BN_ITEM / 2), MC_MASK);
+            } else if (half) {
+              // half entry (128 output channels): 64 weight rows per CTA, fetched with the 64-row box map
+              if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_b[sb], (uint32_t)p.b_stage_bytes);
+              ptx::tma_load_2d_2sm(wdst, &tmW2, lead_full_b + 8u * sb, k0, n0 + (int)cta_rank * (T3_BN / 2));
             } else {
               // pair: this CTA keeps its half of the item's output channels; the MMA reads both halves
               if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_b[sb], 2u * (uint32_t)p.b_stage_bytes);
@@ -306,7 +334,12 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       int it = 0;
-      for (int item = first_item; item < total_items; item += item_stride, ++it) {
+      constexpr uint32_t idesc_half = ptx::make_idesc_bf16(MODE == T3_PAIR ? 256 : 128, T3_BN);
+      for (;; ++it) {
+        int item, ns_only;
+        bool half;
+        if (!entry(it, item, half, ns_only)) break;
+        const uint32_t idesc_e = half ? idesc_half : idesc;
         uint32_t d_tmem[MH];
 #pragma unroll
         for (int h = 0; h < MH; ++h) {
@@ -333,9 +366,9 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                 for (int k = 0; k < T3_BK / 16; ++k) {
                   const uint32_t acc = (k != 0) ? 1u : acc_kb;
                   if constexpr (MODE == T3_PAIR)
-                    ptx::umma_bf16_2sm(d_tmem[h], da + (uint64_t)(h * 1024 + 2 * k), db + (uint64_t)(2 * k), idesc, acc);
+                    ptx::umma_bf16_2sm(d_tmem[h], da + (uint64_t)(h * 1024 + 2 * k), db + (uint64_t)(2 * k), idesc_e, acc);
                   else
-                    ptx::umma_bf16(d_tmem[h], da + (uint64_t)(h * 1024 + 2 * k), db + (uint64_t)(2 * k), idesc, acc);
+                    ptx::umma_bf16(d_tmem[h], da + (uint64_t)(h * 1024 + 2 * k), db + (uint64_t)(2 * k), idesc_e, acc);
                 }
               }
               if constexpr (MODE == T3_SINGLE) ptx::umma_commit(&empty_b[sb]);
@@ -355,9 +388,12 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           }
         }
         if (leader_lane) {
+          // units of this entry: NS for a whole item, one for a half entry (numbered after all whole items)
+          const int u0 = half ? NS * full_rounds + (it - full_rounds) : it * NS;
 #pragma unroll
           for (int ns = 0; ns < NS; ++ns) {
-            const int u = it * NS + ns, k = u / T3_NWG;
+            if (half && ns > 0) break;
+            const int u = u0 + ns, k = u / T3_NWG;
             uint64_t *bar = &ufull[(u - k * T3_NWG) * 2 + (k & 1)];
             if constexpr (MODE == T3_PAIR) ptx::umma_commit_2sm_mc(bar, MC_MASK);
             else ptx::umma_commit(bar);
@@ -387,6 +423,19 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 
     // Residual tiles travel through the staging buffer: the box for unit (item, ns, h) is requested as soon as
     // the previous unit's store has finished reading the buffer.
+    // unit u -> (entry index, item, 128-column sub-tile, half entry?)
+    auto unit = [&](int u, int &j, int &item, int &ns, bool &half) -> bool {
+      int ns_only;
+      if (u < NS * full_rounds) {
+        j = u / NS;
+        ns = u - j * NS;
+        return entry(j, item, half, ns_only);
+      }
+      j = full_rounds + (u - NS * full_rounds);
+      const bool ok = entry(j, item, half, ns_only);
+      ns = ns_only;
+      return ok;
+    };
     auto request_residual = [&](int item, int ns, int h) {
       const int gm = item / n_tiles_n, tn = item - gm * n_tiles_n;
       const int tm = gm * CL + (int)cta_rank;
@@ -395,32 +444,38 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       ptx::tma_load_3d(stg_ptr, &tmR, &res_bar[wg], ch0, tm * p.S_t, h * pos_per_half);
       ptx::tma_load_3d(stg_ptr + 16384, &tmR, &res_bar[wg], ch0 + 64, tm * p.S_t, h * pos_per_half);
     };
-    auto release_acc = [&](int as) {
+    auto release_acc = [&](int as, bool twice) {
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (MODE == T3_PAIR) ptx::mbar_arrive_cluster(tempty0 + 8u * as);
-        else ptx::mbar_arrive(&tempty[as]);
+        // a half entry has one unit where the barrier expects NS: arrive for the missing one too
+        for (int rep = 0; rep < (twice ? 2 : 1); ++rep) {
+          if constexpr (MODE == T3_PAIR) ptx::mbar_arrive_cluster(tempty0 + 8u * as);
+          else ptx::mbar_arrive(&tempty[as]);
+        }
       }
     };
 
     // units: u = it * NS + ns (one 128-column sub-tile of work item `it`, all MH halves); warpgroup wg takes u = wg (mod NWG)
     if (p.has_res && elected) {
-      const int item0 = first_item + (wg / NS) * item_stride;
-      if (item0 < total_items) request_residual(item0, wg % NS, 0);
+      int j0, item0, ns0;
+      bool half0;
+      if (unit(wg, j0, item0, ns0, half0)) request_residual(item0, ns0, 0);
     }
 
     for (int u = wg;; u += T3_NWG) {
-      const int it = u / NS, ns = u - it * NS;
-      const int item = first_item + it * item_stride;
-      if (item >= total_items) break;
+      int it, item, ns;
+      bool half;
+      if (!unit(u, it, item, ns, half)) break;
       if (p.prof) pc_t0 = clock64();
       const int gm = item / n_tiles_n, tn = item - gm * n_tiles_n;
       const int tm = gm * CL + (int)cta_rank;
       const int b0 = tm * p.S_t;
       const bool tile_ok = tm < p.n_mst;
-      const int nu = u + T3_NWG, nit = nu / NS, nns = nu - nit * NS;     // this warpgroup's next unit
-      const int nitem = first_item + nit * item_stride;
+      int nit, nitem = total_items, nns = 0;                             // this warpgroup's next unit
+      bool nhalf;
+      if (!unit(u + T3_NWG, nit, nitem, nns, nhalf)) nitem = total_items;
+      const bool twice = half && NS == 2;
       uint32_t t_addr[MH];
       {
         const int k = u / T3_NWG;
@@ -434,7 +489,7 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         // nothing to write for this super-tile: consume the residual that was prefetched for it and move on
         if (p.has_res) { ptx::mbar_wait(&res_bar[wg], res_phase); res_phase ^= 1; }
 #pragma unroll
-        for (int h = 0; h < MH; ++h) release_acc((it * MH + h) % ACC);
+        for (int h = 0; h < MH; ++h) release_acc((it * MH + h) % ACC, twice);
         ptx::named_bar_sync(1 + wg, 128);
         if (p.has_res && elected && nitem < total_items) request_residual(nitem, nns, 0);
         continue;
@@ -442,7 +497,7 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 
       {
         const int n0 = tn * BN_ITEM + ns * T3_BN;
-        const uint32_t col0 = (uint32_t)(ns * T3_BN);
+        const uint32_t col0 = half ? 0u : (uint32_t)(ns * T3_BN);      // a half entry accumulates in the first 128 columns
         if constexpr (GW > 0) {
           // ---- pass 1: GroupNorm statistics of (conv + bias) over the L positions x GW channels of each sample.
           // This thread's rows (one per half) belong to ONE sample; lanes with equal (lane % S_t) share it.
@@ -584,7 +639,7 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             ptx::sts128u(ad1, make_uint4(ow[4], ow[5], ow[6], ow[7]));
           }
           // this unit no longer needs accumulator h (the barrier counts all units of the item)
-          release_acc((it * MH + h) % ACC);
+          release_acc((it * MH + h) % ACC, twice);
           // staged tile -> global with a TMA store (rows of samples >= B land in workspace padding)
           ptx::fence_proxy_async();
           ptx::named_bar_sync(1 + wg, 128);

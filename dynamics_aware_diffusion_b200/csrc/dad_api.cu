@@ -51,7 +51,7 @@ struct ConvOp {
   // v3 path (conv_t3.cuh): stride-1 convs with position-major tiles
   bool t3 = false;
   int t3_MH = 1, t3_mode = 0, t3_NS = 1, t3_smem = 0;
-  CUtensorMap t3A1, t3A2, t3W, t3R, t3O;
+  CUtensorMap t3A1, t3A2, t3W, t3W2, t3R, t3O;
   ConvT3Params t3p{};
 };
 
@@ -513,6 +513,8 @@ int finish_t3_op(dad_handle *h, ConvOp &op) {
   const int wrows = op.t3_mode == T3_SINGLE ? 128 : op.t3_mode == T3_MCAST ? 64 : 64 * op.t3_NS;
   cuuint32_t box[2] = {64, (cuuint32_t)wrows};
   if ((rc = make_tmap_raw(h, &op.t3W, op.w_b16, 2, dims, strides, box, "weights"))) return rc;
+  cuuint32_t box2[2] = {64, 64};          // half entries of 256-wide items: 64 rows per CTA
+  if ((rc = make_tmap_raw(h, &op.t3W2, op.w_b16, 2, dims, strides, box2, "weights (half)"))) return rc;
   const int pph = 128 / p.S_t;
   if ((rc = make_t3_act_tmap(h, &op.t3O, op.out, p.S_t, pph, "output"))) return rc;
   if ((rc = make_t3_act_tmap(h, &op.t3R, op.res >= 0 ? op.res : op.out, p.S_t, pph, "residual"))) return rc;
@@ -531,7 +533,7 @@ cudaError_t set_t3_attr(int max_optin) {
 template <int GW, int MH, int MODE, int NS>
 int launch_t3(dad_handle *h, const ConvOp &op, const ConvT3Params &p, int grid, cudaStream_t st) {
   cudaError_t e = launch_k(conv_t3_kernel<GW, MH, MODE, NS>, dim3((unsigned)grid), dim3(T3_THREADS), (size_t)op.t3_smem, st,
-                           MODE == T3_SINGLE ? 1 : 2, op.t3A1, op.t3A2, op.t3W, op.t3R, op.t3O, p);
+                           MODE == T3_SINGLE ? 1 : 2, op.t3A1, op.t3A2, op.t3W, op.t3W2, op.t3R, op.t3O, p);
   if (e != cudaSuccess) DAD_FAIL(h, DAD_ERR_CUDA, "conv_t3 launch failed: %s", cudaGetErrorString(e));
   return DAD_OK;
 }
@@ -545,7 +547,12 @@ int enqueue_t3(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
   p.n_mst = cdiv(B, p.S_t);
   const int CL = op.t3_mode == T3_SINGLE ? 1 : 2;
   const int items = cdiv(p.n_mst, CL) * p.n_tiles_n;
-  const int grid = CL * std::min(items, h->sm_count / CL);
+  // 256-wide items: when the last round would leave at most half of the clusters busy, its items are split
+  // into two 128-wide half entries (a half entry costs ~0.75 of a whole one, so only then does it pay)
+  const int n_cl = h->sm_count / CL;
+  const int rem = items % n_cl;
+  p.split_tail = (op.t3_NS == 2 && rem > 0 && 2 * rem <= n_cl && !(p.debug & 128)) ? 1 : 0;
+  const int grid = CL * std::min(p.split_tail && items < n_cl ? 2 * items : items, n_cl);
   int rc = DAD_ERR_INVALID;
 #define T3_CASE(gw, mh, mode, ns) if (op.GW == gw && op.t3_MH == mh && op.t3_mode == mode && op.t3_NS == ns) rc = launch_t3<gw, mh, mode, ns>(h, op, p, grid, st);
   T3_FOR_EACH(T3_CASE)
