@@ -46,6 +46,18 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
 
 
+def ncu_traffic(kernel, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full`
+    summary of the same workload (profiles/ncu_traffic.json, written by tools/summarize_ncu.py); None if absent."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    try:
+        return json.load(open(path)).get(workload, {}).get(kernel)
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
 
@@ -152,8 +164,10 @@ def run_reference(args, w, name):
         "impl": "reference", "metric": "plans/sec", "value": value, "unit": "plans/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "description": w["label"], "B": w["B"], "H": w["H"], "T": T,
-                   "diffusion_steps": S, "policy": "dynamics-aware" if P is not None else "guided"},
+        "config": {"workload": name, "description": w["label"], "B_per_gpu": w["B"], "H": w["H"], "T": T,
+                   "diffusion_steps": S, "policy": "dynamics-aware" if P is not None else "guided",
+                   "unet": "dim=%d mults=%s" % (w["dim"], ",".join(map(str, w["mults"]))),
+                   "noise": "torch.randn on the host", "parallelism": "host cores of one box (rank 0 only)"},
         "cpu_baseline": {"value": value, "unit": "plans/s", "cores": cores, "kind": "port", "sample": sample,
                          "ms_per_diffusion_step_at_sample_B": per_dstep * 1e3},
         "e2e": {"value": value, "unit": "plans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -306,7 +320,7 @@ def main():
             fl = lay["flops_per_sample"] * B
             lay.update(ms=t_ms, tflops=fl / (t_ms * 1e-3) / 1e12)
             table.append(lay)
-            key = (lay["tile_n"], lay["group_width"], lay["L_out"], lay["C_in"] * lay["taps"], lay["C_out"])
+            key = (lay["kernel"], lay["L_out"], lay["C_in"] * lay["taps"], lay["C_out"])
             gk = groups.setdefault(key, {"ms": 0.0, "flops": 0, "count": 0})
             gk["ms"] += t_ms
             gk["flops"] += fl
@@ -316,8 +330,9 @@ def main():
         achieved = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
         line["roofline"] = {
             "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-            "frac": achieved / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"] + " sustained bf16",
-            "kernel": "conv_tc_kernel<%d,%d> L=%d K=%d N=%d x%d per step" % (key[0], key[1], key[2], key[3], key[4], dom["count"]),
+            "frac": achieved / pk["tf_sustained"], "traffic": ncu_traffic(key[0], args.workload),
+            "peak_source": pk["source"] + " sustained bf16",
+            "kernel": "%s L=%d K=%d N=%d x%d per step" % (key[0], key[1], key[2], key[3], dom["count"]),
             "share_of_unet_time": dom["ms"] / unet_ms, "flops_per_launch": dom["flops"] / dom["count"],
             "avg_launch_ms": dom["ms"] / dom["count"],
         }

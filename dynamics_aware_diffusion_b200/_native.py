@@ -42,7 +42,7 @@ class DadInfo(ctypes.Structure):
 class DadLayerDesc(ctypes.Structure):
     _fields_ = [("name", ctypes.c_char * 96), ("L_out", ctypes.c_int32), ("C_in", ctypes.c_int32),
                 ("C_out", ctypes.c_int32), ("taps", ctypes.c_int32), ("tile_n", ctypes.c_int32),
-                ("group_width", ctypes.c_int32), ("flops_per_sample", ctypes.c_int64)]
+                ("group_width", ctypes.c_int32), ("flops_per_sample", ctypes.c_int64), ("kernel", ctypes.c_char * 64)]
 
 
 class DadError(RuntimeError):

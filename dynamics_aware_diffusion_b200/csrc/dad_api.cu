@@ -1402,8 +1402,13 @@ int dad_layer_info(const dad_handle *h, int32_t index, dad_layer_desc *out) {
   out->C_in = op.Cin_real;
   out->C_out = op.g.Cout;
   out->taps = op.g.taps;
-  out->tile_n = op.t3 ? 10000 * op.t3_MH + 1000 * op.t3_mode + 128 * op.t3_NS : op.BN;   /* v3: MH, mode, N per item */
+  out->tile_n = op.t3 ? 128 * op.t3_NS : op.BN;
   out->group_width = op.GW;
+  if (!h->bf16) snprintf(out->kernel, sizeof(out->kernel), "conv_f32_kernel%s", op.gname.empty() ? "" : "+gn_mish_f32_kernel");
+  else if (op.t3) {
+    static const char *modes[3] = {"single", "mcast", "pair"};
+    snprintf(out->kernel, sizeof(out->kernel), "conv_t3_kernel<GW=%d,MH=%d,%s,N=%d>", op.GW, op.t3_MH, modes[op.t3_mode], 128 * op.t3_NS);
+  } else snprintf(out->kernel, sizeof(out->kernel), "conv_tc_kernel<%d,%d>", op.BN, op.GW);
   out->flops_per_sample = 2LL * op.g.L_out * op.g.taps * op.Cin_real * op.g.Cout;
   return DAD_OK;
 }

@@ -194,7 +194,7 @@ class Engine:
             self._ck(self.lib.dad_layer_info(self.handle, i, ctypes.byref(d)))
             out.append({"index": i, "name": d.name.decode(), "L_out": d.L_out, "C_in": d.C_in, "C_out": d.C_out,
                         "taps": d.taps, "tile_n": d.tile_n, "group_width": d.group_width,
-                        "flops_per_sample": d.flops_per_sample})
+                        "flops_per_sample": d.flops_per_sample, "kernel": d.kernel.decode()})
         return out
 
     def time_layer(self, index, B, iters=20):

@@ -178,8 +178,9 @@ int dad_sample_profile(dad_handle *h, float *x, uint64_t seed, uint64_t sample_o
 typedef struct {
   char name[96];            /* state_dict stem of the weight, e.g. "mid_block1.blocks.0.block.0" */
   int32_t L_out, C_in, C_out, taps;
-  int32_t tile_n, group_width;   /* bf16 path: N-tile and GroupNorm width of the kernel instantiation (0 = no GN) */
+  int32_t tile_n, group_width;   /* bf16 path: output channels per work item and GroupNorm width (0 = no GN) */
   int64_t flops_per_sample;      /* 2 * L_out * taps * C_in(real) * C_out */
+  char kernel[64];               /* kernel instantiation that executes the layer, e.g. "conv_t3_kernel<64,1,pair,256>" */
 } dad_layer_desc;
 int dad_layer_count(const dad_handle *h);
 int dad_layer_info(const dad_handle *h, int32_t index, dad_layer_desc *out);
