@@ -27,6 +27,12 @@ CASES = {
     # projector-GEMM path; linear beta schedule; 'linear' projection schedule
     "cheetah_s": dict(n=17, m=6, dim=64, mults=(1, 4, 8), H=32, S=6, B=2, beta="linear", dyn="data_driven",
                       proj_schedule="linear", strength=0.8, wseed=103),
+    # longer horizons of the scaling sweep (H = 64 / 128): GroupNorm rows of one sample span several warps / the
+    # whole 128-row tile
+    "h64": dict(n=4, m=2, dim=64, mults=(1, 2, 4), H=64, S=5, B=3, beta="cosine", dyn="double_integrator",
+                proj_schedule="constant", strength=0.5, wseed=105),
+    "h128": dict(n=4, m=2, dim=64, mults=(1, 2), H=128, S=4, B=2, beta="linear", dyn="double_integrator",
+                 proj_schedule="noise_schedule", strength=1.0, wseed=106),
     # Door-shaped transitions, four levels (bottleneck length 4); 'quadratic' projection schedule
     "door_s": dict(n=39, m=28, dim=64, mults=(1, 2, 4, 8), H=32, S=4, B=2, beta="cosine", dyn="data_driven",
                    proj_schedule="quadratic", strength=1.0, wseed=104),

@@ -22,6 +22,10 @@ FREE_TOL = {"fp32": 2e-4, "bf16": 5e-2}
 # well-conditioned step and to ILL_TOL on that one, and its eps error must not exceed stock autocast-bf16
 # PyTorch's on the same input (test_bf16_unet_no_worse_than_stock_autocast).
 ILL_TOL = 5e-2
+# Raw U-Net output (eps) in bf16: the tolerance of BASELINE.json is on x per step; eps itself carries the bf16
+# rounding of ~35 layers (ours 0.8-1.05e-2, stock torch.autocast 1.1-1.3e-2 on the same inputs) and is held to
+# 1.5e-2 here and to <= 1.1x stock autocast in test_bf16_unet_no_worse_than_stock_autocast.
+EPS_TOL = {"fp32": 1e-5, "bf16": 1.5e-2}
 CASE_NAMES = list(helpers.CASES)
 
 
@@ -87,9 +91,9 @@ def test_unet_forward(name, precision):
     x = cu(g["x_init"])
     for i, want in zip(g["unet_steps"], g["unet_eps"]):
         got = dif.model(x, torch.full((c["B"],), int(i), device=x.device, dtype=torch.long))
-        assert helpers.rel_l2(got.cpu().numpy(), want) < TOL[precision], "step %d" % i
+        assert helpers.rel_l2(got.cpu().numpy(), want) < EPS_TOL[precision], "step %d" % i
     got = dif.model(x, cu(g["unet_t_rows"]))
-    assert helpers.rel_l2(got.cpu().numpy(), g["unet_eps_rows"]) < TOL[precision]
+    assert helpers.rel_l2(got.cpu().numpy(), g["unet_eps_rows"]) < EPS_TOL[precision]
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
