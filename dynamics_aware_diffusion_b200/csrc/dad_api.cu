@@ -109,7 +109,8 @@ struct dad_handle {
   // host-buffer path
   float *d_hostx = nullptr, *d_hostnoise = nullptr;
   size_t hostx_cap = 0, hostnoise_cap = 0;
-  cudaStream_t cap_stream = nullptr, own_stream = nullptr;
+  cudaStream_t cap_stream = nullptr, own_stream = nullptr, side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::map<long long, GraphEntry> graphs;
   long long launches = 0;            // total kernels launched
   long long counting = 0;            // kernels enqueued since last reset (capture accounting)
@@ -652,7 +653,19 @@ int enqueue_f32(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
 }
 
 // One U-Net forward of the staged trajectories -> d_eps.  (TemporalUnet.forward, temporal_unet.py:199-241)
-int enqueue_unet(dad_handle *h, int B, cudaStream_t st, bool advance = false) {
+// In the captured step, kernels that do not depend on each other are put on a forked branch of the graph: a
+// block's 1x1 residual conv beside its first k5 conv (both read the block input), and the two phases of a
+// ConvTranspose.  Every kernel is persistent over all SMs, so the branch kernel's CTAs move in exactly while the
+// main kernel's tail drains its SMs.
+bool forks_with_next(const dad_handle *h, size_t i) {
+  if (!h->bf16 || i + 1 >= h->ops.size()) return false;
+  const ConvOp &a = h->ops[i], &b = h->ops[i + 1];
+  if (b.wname.find("residual_conv") != std::string::npos && b.in1 == a.in1 && b.in2 == a.in2) return true;
+  if (a.transposed && b.transposed && a.out == b.out && a.g.out_phase != b.g.out_phase) return true;
+  return false;
+}
+
+int enqueue_unet(dad_handle *h, int B, cudaStream_t st, bool advance = false, cudaStream_t side = nullptr) {
   const dad_config &c = h->cfg;
   const size_t rows = (size_t)B * c.horizon;
   if (h->bf16) {
@@ -665,7 +678,19 @@ int enqueue_unet(dad_handle *h, int B, cudaStream_t st, bool advance = false) {
              (__nv_bfloat16 *)nullptr, rows, c.transition_dim, 0, advance ? 1 : 0);
   }
   h->counting += 1;
-  for (const ConvOp &op : h->ops) {
+  for (size_t i = 0; i < h->ops.size(); ++i) {
+    const ConvOp &op = h->ops[i];
+    if (side && forks_with_next(h, i)) {
+      CK(h, cudaEventRecord(h->ev_fork, st));
+      CK(h, cudaStreamWaitEvent(side, h->ev_fork, 0));
+      int rc = enqueue_tc(h, op, B, st);
+      if (!rc) rc = enqueue_tc(h, h->ops[i + 1], B, side);
+      if (rc) return rc;
+      CK(h, cudaEventRecord(h->ev_join, side));
+      CK(h, cudaStreamWaitEvent(st, h->ev_join, 0));
+      ++i;
+      continue;
+    }
     int rc = h->bf16 ? enqueue_tc(h, op, B, st) : enqueue_f32(h, op, B, st);
     if (rc) return rc;
   }
@@ -792,7 +817,8 @@ int get_graph(dad_handle *h, int B, bool project, GraphEntry **out) {
   h->counting = 0;
   CK(h, cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
   // captured step: [stage x, step index -= 1] -> U-Net -> fused step kernel; the loop starts one index high
-  int rc = enqueue_unet(h, B, h->cap_stream, true);
+  const bool fork = !(getenv("DAD_FORK") && atoi(getenv("DAD_FORK")) == 0);
+  int rc = enqueue_unet(h, B, h->cap_stream, true, fork ? h->side_stream : nullptr);
   if (!rc) rc = enqueue_step(h, h->d_eps, B, project, false, h->cap_stream);
   cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
   if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -922,7 +948,10 @@ int dad_create(const dad_config *cfg, dad_handle **out) {
   int rc = build_plan(h);
   if (rc) return fail(rc);
   if ((rc = set_kernel_attrs(h))) return fail(rc);
-  if (cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
+  if (cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     h->err = "cudaStreamCreate failed";
     return fail(DAD_ERR_CUDA);
@@ -978,6 +1007,9 @@ int dad_destroy(dad_handle *h) {
   drop_graphs(h);
   for (void *p : h->allocs) cudaFree(p);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return DAD_OK;
