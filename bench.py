@@ -117,6 +117,23 @@ def projector_inputs(w):
     return ProjectionMatrixBuilder(A, B, w["n"], w["m"]).get_projection_matrix(w["H"]), nz
 
 
+def stream_step_roofline(dev, pk, B=65536, H=32, T=6):
+    """K7 (x0, clamp, posterior mean, Philox noise, inpainting; no projector) at B=65536: 12*H*T*B = 151 MB per launch."""
+    import torch
+    from dynamics_aware_diffusion_b200 import TemporalUnet, GaussianDiffusion, _native as N
+    net = TemporalUnet(T, dim=64, dim_mults=(1,), precision="fp32", max_batch=B)      # small arena; the U-Net is not run
+    dif = GaussianDiffusion(net, horizon=H, observation_dim=T - 2, action_dim=2, n_timesteps=100).to(dev)
+    eng = dif.engine(H, dev)
+    eng.set_conditions({0: torch.zeros(1, T, device=dev)}, B)
+    ms = eng.time_step_kernel(B, 50, flags=N.FLAG_CONDITIONS, iters=20)
+    nbytes = 12 * H * T * B
+    del eng, dif, net
+    torch.cuda.empty_cache()
+    return {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+            "frac": nbytes / (ms * 1e-3) / 1e9 / pk["hbm"], "avg_launch_ms": ms, "bytes_per_launch": nbytes,
+            "kernel": "step_pointwise_kernel", "workload": "B=%d H=%d T=%d, Philox noise, start inpainting" % (B, H, T)}
+
+
 def run_reference(args, w, name):
     """The reference's CPU sampler (its op sequence restated in torch, oracle/torch_port.py) on the host cores."""
     import numpy as np
@@ -343,6 +360,12 @@ def main():
             "bound": "hbm", "achieved": st_bytes / (st_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
             "frac": st_bytes / (st_ms * 1e-3) / 1e9 / pk["hbm"], "traffic": None, "avg_launch_ms": st_ms,
             "bytes_per_launch": st_bytes, "note": "working set %.1f MB is L2-resident at this B" % (st_bytes / 1e6)}
+        # the same memory-bound step kernel without a projector (guided / plain policy) on a batch whose working set
+        # leaves the L2 (the HBM fraction is only observable there)
+        try:
+            line["roofline_step_kernel_stream"] = stream_step_roofline(dev, pk)
+        except Exception as exc:      # measurement extra: never fail the bench line over it
+            line["roofline_step_kernel_stream"] = {"error": str(exc)[:200]}
         line["unet_ms_sum_of_layers"] = unet_ms
         if args.layers_out:
             os.makedirs(os.path.dirname(os.path.abspath(args.layers_out)), exist_ok=True)

@@ -147,6 +147,22 @@ int dev_alloc(dad_handle *h, T **p, size_t n) {
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Set-up copy (host or device source) that has fully landed when the call returns.  A plain cudaMemcpy from
+// pageable host memory may return while the DMA is still in flight on the legacy stream, and the library's
+// kernels run on non-blocking streams that do not wait for it.
+// Same for fills: cudaMemset runs asynchronously on the legacy stream, which the library's streams do not wait on.
+inline cudaError_t fill_now(void *dst, int value, size_t bytes, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(dst, value, bytes, st);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(st);
+}
+
+inline cudaError_t copy_now(void *dst, const void *src, size_t bytes, cudaStream_t st) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(st);
+}
+
 // Every kernel of the sampling step is launched with programmatic stream serialization: it may start (and run
 // its set-up) while its predecessor drains, and calls griddepcontrol.wait before touching global data.
 // DAD_PDL=0 disables the attribute (plain stream order).
@@ -851,7 +867,7 @@ int device_view(dad_handle *h, const dad_tensor *t, float *stage, const float **
     return DAD_OK;
   }
   cudaGetLastError();
-  CK(h, cudaMemcpy(stage, t->data, t->numel * sizeof(float), cudaMemcpyDefault));
+  CK(h, copy_now(stage, t->data, t->numel * sizeof(float), h->own_stream));
   *out = stage;
   return DAD_OK;
 }
@@ -959,15 +975,15 @@ int dad_create(const dad_config *cfg, dad_handle **out) {
   // workspaces
   const size_t arena_bytes = h->act_bytes_per_sample * (size_t)c.max_batch;
   if ((rc = dev_alloc(h, &h->arena, arena_bytes))) return fail(rc);
-  cudaMemset(h->arena, 0, arena_bytes);
+  fill_now(h->arena, 0, arena_bytes, h->own_stream);
   if ((rc = dev_alloc(h, &h->d_eps, (size_t)c.max_batch * h->D))) return fail(rc);
   if ((rc = dev_alloc(h, &h->d_xtmp, (size_t)c.max_batch * h->D))) return fail(rc);
   if ((rc = dev_alloc(h, &h->d_ls, 1))) return fail(rc);
-  cudaMemset(h->d_ls, 0, sizeof(LoopState));
+  fill_now(h->d_ls, 0, sizeof(LoopState), h->own_stream);
   for (int i = 0; i < 5; ++i)
     if ((rc = dev_alloc(h, &h->d_sched[i], (size_t)c.n_timesteps))) return fail(rc);
   if ((rc = dev_alloc(h, &h->d_alpha, (size_t)c.n_timesteps))) return fail(rc);
-  cudaMemset(h->d_alpha, 0, sizeof(float) * c.n_timesteps);
+  fill_now(h->d_alpha, 0, sizeof(float) * c.n_timesteps, h->own_stream);
   h->cond_cap = (size_t)kMaxCond * c.transition_dim;
   if ((rc = dev_alloc(h, &h->d_cond, h->cond_cap))) return fail(rc);
   // per-op parameter storage
@@ -980,7 +996,7 @@ int dad_create(const dad_config *cfg, dad_handle **out) {
       if ((rc = dev_alloc(h, &op.w_f32, (size_t)op.g.taps * op.Cin_store * op.g.Cout))) return fail(rc);
     }
     if ((rc = dev_alloc(h, &op.bias, (size_t)op.Cout_pad))) return fail(rc);
-    cudaMemset(op.bias, 0, sizeof(float) * op.Cout_pad);
+    fill_now(op.bias, 0, sizeof(float) * op.Cout_pad, h->own_stream);
     if (!op.gname.empty()) {
       if ((rc = dev_alloc(h, &op.gamma, (size_t)op.g.Cout))) return fail(rc);
       if ((rc = dev_alloc(h, &op.beta, (size_t)op.g.Cout))) return fail(rc);
@@ -1048,13 +1064,13 @@ int dad_load_weights(dad_handle *h, const dad_tensor *tensors, int32_t n) {
                                                           op.sel, op.transposed);
     }
     CK(h, cudaStreamSynchronize(st));   // `stage` is reused by the next tensor
-    CK(h, cudaMemcpy(op.bias, b->data, sizeof(float) * op.g.Cout, cudaMemcpyDefault));
+    CK(h, copy_now(op.bias, b->data, sizeof(float) * op.g.Cout, h->own_stream));
     if (!op.gname.empty()) {
       const dad_tensor *gw = nt.get(op.gname + ".weight"), *gb = nt.get(op.gname + ".bias");
       if ((rc = check_dims(h, gw, op.gname + ".weight", op.g.Cout))) return done(rc);
       if ((rc = check_dims(h, gb, op.gname + ".bias", op.g.Cout))) return done(rc);
-      CK(h, cudaMemcpy(op.gamma, gw->data, sizeof(float) * op.g.Cout, cudaMemcpyDefault));
-      CK(h, cudaMemcpy(op.beta, gb->data, sizeof(float) * op.g.Cout, cudaMemcpyDefault));
+      CK(h, copy_now(op.gamma, gw->data, sizeof(float) * op.g.Cout, h->own_stream));
+      CK(h, copy_now(op.beta, gb->data, sizeof(float) * op.g.Cout, h->own_stream));
     }
   }
   // ---- time tables: every step index, once (K6)
@@ -1077,11 +1093,11 @@ int dad_load_weights(dad_handle *h, const dad_tensor *tensors, int32_t n) {
     sinusoid_table_kernel<<<cdiv((long long)S * (dim / 2), 256), 256, 0, st>>>(emb, S, dim);
     const float *wd = nullptr;
     if ((rc = device_view(h, w1, stage, &wd))) { cudaFree(bd); return done2(rc); }
-    cudaMemcpy(bd, b1->data, sizeof(float) * td * 4, cudaMemcpyDefault);
+    copy_now(bd, b1->data, sizeof(float) * td * 4, h->own_stream);
     linear_rows_kernel<<<cdiv((long long)S * td * 4, 256), 256, 0, st>>>(emb, wd, bd, h1, S, dim, td * 4, 0, 1);
     cudaStreamSynchronize(st);
     if ((rc = device_view(h, w3, stage, &wd))) { cudaFree(bd); return done2(rc); }
-    cudaMemcpy(bd, b3->data, sizeof(float) * td, cudaMemcpyDefault);
+    copy_now(bd, b3->data, sizeof(float) * td, h->own_stream);
     linear_rows_kernel<<<cdiv((long long)S * td, 256), 256, 0, st>>>(h1, wd, bd, temb, S, td * 4, td, 0, 0);
     cudaStreamSynchronize(st);
     cudaFree(bd);
@@ -1094,7 +1110,7 @@ int dad_load_weights(dad_handle *h, const dad_tensor *tensors, int32_t n) {
     if ((rc = device_view(h, w, stage, &wd))) return done2(rc);
     float *bd = nullptr;
     CK(h, cudaMalloc(&bd, sizeof(float) * tb.C));
-    cudaMemcpy(bd, b->data, sizeof(float) * tb.C, cudaMemcpyDefault);
+    copy_now(bd, b->data, sizeof(float) * tb.C, h->own_stream);
     linear_rows_kernel<<<cdiv((long long)S * tb.C, 256), 256, 0, st>>>(temb, wd, bd, tb.tab, S, td, tb.C, 1, 0);
     cudaStreamSynchronize(st);
     cudaFree(bd);
@@ -1112,7 +1128,7 @@ int dad_set_schedule(dad_handle *h, const float *sr, const float *srm1, const fl
   if (n != h->cfg.n_timesteps) DAD_FAIL(h, DAD_ERR_INVALID, "schedule length %d != n_timesteps %d", n, h->cfg.n_timesteps);
   CK(h, cudaSetDevice(h->cfg.device));
   const float *src[5] = {sr, srm1, c1, c2, lv};
-  for (int i = 0; i < 5; ++i) CK(h, cudaMemcpy(h->d_sched[i], src[i], sizeof(float) * n, cudaMemcpyDefault));
+  for (int i = 0; i < 5; ++i) CK(h, copy_now(h->d_sched[i], src[i], sizeof(float) * n, h->own_stream));
   h->have_sched = true;
   return DAD_OK;
 }
@@ -1131,9 +1147,9 @@ int dad_set_projector(dad_handle *h, const float *Nmat, const float *q, const fl
     if ((rc = dev_alloc(h, &h->d_q, (size_t)D))) return rc;
     drop_graphs(h);   // new buffers -> captured pointers are stale
   }
-  CK(h, cudaMemcpy(h->d_Nrow, Nmat, sizeof(float) * D * D, cudaMemcpyDefault));
-  CK(h, cudaMemcpy(h->d_q, q, sizeof(float) * D, cudaMemcpyDefault));
-  CK(h, cudaMemcpy(h->d_alpha, alpha, sizeof(float) * n, cudaMemcpyDefault));
+  CK(h, copy_now(h->d_Nrow, Nmat, sizeof(float) * D * D, h->own_stream));
+  CK(h, copy_now(h->d_q, q, sizeof(float) * D, h->own_stream));
+  CK(h, copy_now(h->d_alpha, alpha, sizeof(float) * n, h->own_stream));
   // transpose on device via the fp32 packer: treat Nmat as a (Cout=D, Cin=D, k=1) conv weight -> [c][n]
   TapSel sel{};
   pack_w_f32_kernel<<<cdiv((long long)D * D, 256), 256, 0, h->own_stream>>>(h->d_Nrow, h->d_Nt, D, D, 1, 1, sel, 0);
@@ -1147,7 +1163,7 @@ int dad_set_projector(dad_handle *h, const float *Nmat, const float *q, const fl
       if ((rc = dev_alloc(h, &h->d_projW, (size_t)Np * 3 * Kp))) return rc;
       if ((rc = dev_alloc(h, &h->d_split, (size_t)h->cfg.max_batch * 3 * Kp))) return rc;
       if ((rc = dev_alloc(h, &h->d_qpad, (size_t)Np))) return rc;
-      CK(h, cudaMemset(h->d_split, 0, sizeof(__nv_bfloat16) * (size_t)h->cfg.max_batch * 3 * Kp));
+      CK(h, fill_now(h->d_split, 0, sizeof(__nv_bfloat16) * (size_t)h->cfg.max_batch * 3 * Kp, h->own_stream));
       h->projKp = Kp;
       h->projNp = Np;
       // A: (3Kp, 1, 1, max_batch) boxes of 64 x 128 rows; W: (3Kp, Np) boxes of 64 x 128
@@ -1161,8 +1177,8 @@ int dad_set_projector(dad_handle *h, const float *Nmat, const float *q, const fl
       cuuint32_t wb[2] = {64, 128};
       if ((rc2 = make_tmap(h, &h->tmProjW, h->d_projW, 2, wd, ws, wb))) return rc2;
     }
-    CK(h, cudaMemset(h->d_qpad, 0, sizeof(float) * h->projNp));
-    CK(h, cudaMemcpy(h->d_qpad, h->d_q, sizeof(float) * D, cudaMemcpyDeviceToDevice));
+    CK(h, fill_now(h->d_qpad, 0, sizeof(float) * h->projNp, h->own_stream));
+    CK(h, copy_now(h->d_qpad, h->d_q, sizeof(float) * D, h->own_stream));
     pack_projector_bf16_kernel<<<cdiv((long long)h->projNp * h->projKp, 256), 256, 0, h->own_stream>>>(
         h->d_Nrow, h->d_projW, D, h->projKp, h->projNp);
     CK(h, cudaStreamSynchronize(h->own_stream));
@@ -1191,7 +1207,7 @@ int dad_set_conditions(dad_handle *h, const int32_t *h_idx, const float *vals, i
     h->cond_cap = need;
     drop_graphs(h);
   }
-  CK(h, cudaMemcpy(h->d_cond, vals, sizeof(float) * need, cudaMemcpyDefault));
+  CK(h, copy_now(h->d_cond, vals, sizeof(float) * need, h->own_stream));
   h->n_cond = n_cond;
   h->cond_per_batch = per_batch ? 1 : 0;
   h->cond_B = per_batch ? B : 1;
@@ -1461,7 +1477,7 @@ int dad_time_layer(dad_handle *h, int32_t index, int32_t B, int32_t iters, float
   unsigned long long *prof = nullptr;
   if (h->bf16 && getenv("DAD_TC_PROF")) {
     CK(h, cudaMalloc(&prof, 4 * sizeof(unsigned long long)));
-    CK(h, cudaMemset(prof, 0, 4 * sizeof(unsigned long long)));
+    CK(h, fill_now(prof, 0, 4 * sizeof(unsigned long long), h->own_stream));
     op.tcp.prof = prof;
     op.t3p.prof = prof;
   }

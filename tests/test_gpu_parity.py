@@ -258,3 +258,51 @@ def test_sample_host_c_abi(name):
     z = torch.from_numpy(np.array(g["noise"])).pin_memory()
     eng.sample_host(x, c["S"], noise_seq_host=z, flags=flags)
     assert helpers.rel_l2(x.numpy(), g["trace_dyn"][-1]) < FREE_TOL["fp32"]
+
+
+def test_raw_c_abi_sampling():
+    """The C ABI with nothing but ctypes (include/dad_b200.h as a non-PyTorch host would bind it):
+    dad_create -> dad_load_weights -> dad_set_schedule -> dad_set_conditions -> dad_sample_host, checked against
+    the reference's conditioned trace; then the error convention."""
+    import ctypes
+    from dynamics_aware_diffusion_b200 import _native as N
+    c = helpers.CASES["tiny"]
+    g = helpers.load_golden("tiny")
+    sd, _ = helpers.make_state_dict(c)
+    L = N.lib()
+    cfg = N.DadConfig(abi_version=N.DAD_ABI_VERSION, device=0, precision=N.PRECISION_FP32, transition_dim=6, dim=c["dim"],
+                      n_levels=len(c["mults"]), kernel_size=5, time_dim=0, horizon=c["H"], n_timesteps=c["S"],
+                      predict_epsilon=1, clip_denoised=1, max_batch=8)
+    for i, m in enumerate(c["mults"]):
+        cfg.dim_mults[i] = m
+    h = ctypes.c_void_p()
+    assert L.dad_create(ctypes.byref(cfg), ctypes.byref(h)) == 0
+    try:
+        unet = {k[len("model."):]: np.ascontiguousarray(v, dtype=np.float32) for k, v in sd.items() if k.startswith("model.")}
+        names = [k.encode() for k in unet]
+        arr = (N.DadTensor * len(unet))()
+        for i, (nm, v) in enumerate(zip(names, unet.values())):
+            arr[i].name, arr[i].data, arr[i].numel = nm, v.ctypes.data, v.size        # HOST pointers are accepted
+        assert L.dad_load_weights(h, arr, len(unet)) == 0
+        bufs = [np.ascontiguousarray(sd[k], dtype=np.float32) for k in
+                ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
+                 "posterior_mean_coef2", "posterior_log_variance_clipped")]
+        assert L.dad_set_schedule(h, *[ctypes.c_void_p(b.ctypes.data) for b in bufs], c["S"]) == 0
+        hidx = (ctypes.c_int32 * 2)(0, -1)                                        # python-style negative index = goal
+        vals = np.ascontiguousarray(np.stack([g["start"], g["goal"]]), dtype=np.float32)
+        assert L.dad_set_conditions(h, hidx, ctypes.c_void_p(vals.ctypes.data), 2, 0, c["B"]) == 0
+        x = np.array(g["x_init"], dtype=np.float32)
+        z = np.ascontiguousarray(g["noise"], dtype=np.float32)
+        rc = L.dad_sample_host(h, ctypes.c_void_p(x.ctypes.data), ctypes.c_void_p(z.ctypes.data), 0, 0, c["B"], c["S"],
+                               N.FLAG_CONDITIONS)
+        assert rc == 0, L.dad_last_error(h)
+        assert helpers.rel_l2(x, g["trace_cond"][-1]) < FREE_TOL["fp32"]
+        # errors: negative status + message, nothing thrown
+        assert L.dad_sample_host(h, ctypes.c_void_p(x.ctypes.data), None, 0, 0, c["B"], c["S"] + 1, 0) == N.ERR_INVALID
+        assert b"n_steps" in L.dad_last_error(h)
+        assert L.dad_step(h, None, None, None, None, 0.0, 0, 0, 0, 0, 1, None) == N.ERR_INVALID
+        info = N.DadInfo()
+        assert L.dad_get_info(h, ctypes.byref(info)) == 0 and info.n_conv_layers > 0 and info.sm_count > 0
+        assert L.dad_launch_count(h) > 0
+    finally:
+        assert L.dad_destroy(h) == 0
