@@ -125,13 +125,18 @@ def stream_step_roofline(dev, pk, B=65536, H=32, T=6):
     dif = GaussianDiffusion(net, horizon=H, observation_dim=T - 2, action_dim=2, n_timesteps=100).to(dev)
     eng = dif.engine(H, dev)
     eng.set_conditions({0: torch.zeros(1, T, device=dev)}, B)
-    ms = eng.time_step_kernel(B, 50, flags=N.FLAG_CONDITIONS, iters=20)
-    nbytes = 12 * H * T * B
+    out = {"bound": "hbm", "peak": pk["hbm"], "unit": "GB/s", "kernel": "step_pointwise_kernel",
+           "workload": "B=%d H=%d T=%d, start inpainting" % (B, H, T)}
+    # in-kernel Philox noise: 12 B/element (read x, eps; write x); injected noise (parity mode): 16 B/element
+    for key, extra, per_elt in (("philox", 0, 12), ("injected_noise", 0x100, 16)):
+        ms = eng.time_step_kernel(B, 50, flags=N.FLAG_CONDITIONS | extra, iters=20)
+        nbytes = per_elt * H * T * B
+        out[key] = {"achieved": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / pk["hbm"],
+                    "avg_launch_ms": ms, "bytes_per_launch": nbytes}
+    out["achieved"], out["frac"] = out["injected_noise"]["achieved"], out["injected_noise"]["frac"]
     del eng, dif, net
     torch.cuda.empty_cache()
-    return {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-            "frac": nbytes / (ms * 1e-3) / 1e9 / pk["hbm"], "avg_launch_ms": ms, "bytes_per_launch": nbytes,
-            "kernel": "step_pointwise_kernel", "workload": "B=%d H=%d T=%d, Philox noise, start inpainting" % (B, H, T)}
+    return out
 
 
 def run_reference(args, w, name):

@@ -1512,11 +1512,22 @@ int dad_time_step_kernel(dad_handle *h, int32_t B, int32_t step, uint32_t flags,
     h->hostx_cap = n;
   }
   CK(h, cudaMemsetAsync(h->d_hostx, 0, n * sizeof(float), st));
+  const bool injected = (flags & 0x100u) != 0;      // measurement only: read the noise from a buffer instead of Philox
+  flags &= ~0x100u;
+  if (injected) {
+    if (n > h->hostnoise_cap) {
+      int rc;
+      if ((rc = dev_alloc(h, &h->d_hostnoise, n))) return rc;
+      h->hostnoise_cap = n;
+    }
+    CK(h, cudaMemsetAsync(h->d_hostnoise, 0, n * sizeof(float), st));
+  }
   LoopState ls{};
   ls.step = step;
   ls.n_steps = step + 1;
   ls.flags = flags;
   ls.x = h->d_hostx;
+  ls.noise = injected ? h->d_hostnoise : nullptr;
   ls.seed = 1;
   fill_cond(h, ls, 0);
   int rc = set_loop_state(h, ls, st);

@@ -44,7 +44,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   return ctr;
 }
 
-// Four standard normals from one Philox block (Box-Muller on two pairs).
+// Four standard normals from one Philox block (Box-Muller on two pairs).  The transcendental part uses the SFU
+// approximations (lg2 / sqrt / sin / cos .approx, |error| ~1e-6): the generator sits inside a kernel that must
+// stream at HBM speed, and the library-precision versions cost ~4x the instructions.
 __device__ __forceinline__ float4 philox_normal4(unsigned quad, unsigned slot, unsigned long long sample,
                                                  unsigned long long seed) {
   const uint4 r = philox4x32_10(make_uint4(quad, slot, (unsigned)sample, (unsigned)(sample >> 32)),
@@ -52,10 +54,13 @@ __device__ __forceinline__ float4 philox_normal4(unsigned quad, unsigned slot, u
   const float k = 2.3283064365386963e-10f;  // 2^-32
   const float u0 = ((float)r.x + 0.5f) * k, u1 = ((float)r.y + 0.5f) * k;
   const float u2 = ((float)r.z + 0.5f) * k, u3 = ((float)r.w + 0.5f) * k;
-  const float r0 = sqrtf(-2.f * logf(u0)), r1 = sqrtf(-2.f * logf(u2));
+  float r0, r1;
+  // sqrt(-2 ln u) = sqrt(-2 ln2 * lg2 u)
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(-1.3862943611198906f * __log2f(u0)));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(-1.3862943611198906f * __log2f(u2)));
   float s0, c0, s1, c1;
-  sincospif(2.f * u1, &s0, &c0);
-  sincospif(2.f * u3, &s1, &c1);
+  __sincosf(6.283185307179586f * u1, &s0, &c0);
+  __sincosf(6.283185307179586f * u3, &s1, &c1);
   return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
 }
 
@@ -122,13 +127,16 @@ __device__ __forceinline__ void step_pointwise4(const StepParams &p, const LoopS
   }
 }
 
+// x[:, h] = val for every registered (h, val): element d of the flattened (H*T) sample belongs to condition c
+// iff 0 <= d - h_c*T < T (no division: this runs per element inside a bandwidth-bound kernel).
 __device__ __forceinline__ float cond_override(const LoopState &ls, const float *cond_vals, int n_cond, int b,
                                                int d, int T, float v) {
-  const int hh = d / T, tt = d - hh * T;
-  for (int c = 0; c < n_cond; ++c)
-    if (ls.cond_h[c] == hh)
+  for (int c = 0; c < n_cond; ++c) {
+    const unsigned tt = (unsigned)(d - ls.cond_h[c] * T);
+    if (tt < (unsigned)T)
       v = cond_vals[((size_t)c * (ls.cond_per_batch ? ls.cond_B : 1) +
                      (ls.cond_per_batch ? (ls.cond_row0 + b) : 0)) * T + tt];
+  }
   return v;
 }
 
@@ -147,11 +155,17 @@ __global__ void __launch_bounds__(256) step_pointwise_kernel(const StepParams p)
   float *dst = p.to_tmp ? p.xtmp : ls.x;
   float *tr = (!p.to_tmp && ls.trace) ? ls.trace + (size_t)(ls.n_steps - 1 - i) * ls.trace_stride : nullptr;
   const size_t total4 = (size_t)p.B * p.D / 4;
-  for (size_t q4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q4 < total4;
-       q4 += (size_t)gridDim.x * blockDim.x) {
+  // (sample, offset) of this thread's float4 advance by a fixed stride: one division up front, none in the loop
+  const unsigned D4 = (unsigned)p.D / 4u;
+  const size_t stride4 = (size_t)gridDim.x * blockDim.x;
+  const unsigned sb = (unsigned)(stride4 / D4), sd = (unsigned)(stride4 - (size_t)sb * D4);
+  size_t q4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned b_u = (unsigned)(q4 / D4), d4 = (unsigned)(q4 - (size_t)b_u * D4);
+  for (; q4 < total4; q4 += stride4, b_u += sb, d4 += sd) {
+    if (d4 >= D4) { d4 -= D4; b_u += 1; }
     const size_t e = q4 * 4;
-    const int b = (int)(e / p.D);
-    const int d0 = (int)(e - (size_t)b * p.D);
+    const int b = (int)b_u;
+    const int d0 = (int)(d4 * 4u);
     float o[4];
     step_pointwise4(p, ls, b, d0, cr, crm1, c1, c2, sig, gvar, o);
     if (n_cond) {

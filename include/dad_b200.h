@@ -188,7 +188,8 @@ int dad_layer_info(const dad_handle *h, int32_t index, dad_layer_desc *out);
  * untimed launch); *ms_per_launch receives the average.  Operates on the handle's own workspaces (their
  * contents are whatever the last forward left there).  Synchronises. */
 int dad_time_layer(dad_handle *h, int32_t index, int32_t B, int32_t iters, float *ms_per_launch, void *stream);
-/* Same for the fused step kernel(s) (K7 [+K8]) at step index `step`, Philox noise, on scratch trajectories. */
+/* Same for the fused step kernel(s) (K7 [+K8]) at step index `step` on scratch trajectories; Philox noise, or a
+ * noise buffer when flags has bit 0x100 set (the parity-mode data path: 16 instead of 12 bytes per element). */
 int dad_time_step_kernel(dad_handle *h, int32_t B, int32_t step, uint32_t flags, int32_t iters,
                          float *ms_per_launch, void *stream);
 
