@@ -32,7 +32,10 @@ constexpr int T3_NB = 4;            // weight-tile ring
 #endif
 constexpr int T3_NWG = DAD_T3_NWG;  // epilogue warpgroups; each takes every T3_NWG-th 128-column unit
 constexpr int T3_THREADS = 64 + 128 * T3_NWG;     // producer, MMA issuer, epilogue warpgroups
-constexpr int T3_STAGE_OUT = 128 * T3_BN * 2;          // 32 KB bf16 staging per epilogue warpgroup
+// epilogue unit width in columns: 64 where the GroupNorm width allows it (finer units = shorter accumulator
+// residency and tails, half the staging memory), 128 for GroupNorm width 128
+__host__ __device__ constexpr int t3_unit_cols(int gw) { return gw == 128 ? 128 : 64; }
+__host__ __device__ constexpr int t3_stage_out_bytes(int gw) { return 128 * t3_unit_cols(gw) * 2; }   // bf16 staging per warpgroup
 // MODE: how the CTAs of a launch cooperate
 constexpr int T3_SINGLE = 0;        // one CTA per tile, tcgen05 cta_group::1
 constexpr int T3_MCAST = 1;         // 2-CTA cluster, neighbouring M tiles, weight tiles multicast (cta_group::1)
@@ -66,15 +69,16 @@ struct T3Smem {
   int a_ring, b_ring, stage_out, bars, params, scratch, total;
 };
 
-__host__ __device__ inline T3Smem t3_smem_layout(int a_stage_bytes, int n_a, int b_stage_bytes, int cout_pad, int S_t, int ng) {
+__host__ __device__ inline T3Smem t3_smem_layout(int a_stage_bytes, int n_a, int b_stage_bytes, int cout_pad, int S_t, int gw) {
+  const int ng = gw > 0 ? t3_unit_cols(gw) / gw : 1;
   T3Smem s;
   s.a_ring = 0;
   s.b_ring = s.a_ring + n_a * a_stage_bytes;
   s.stage_out = s.b_ring + T3_NB * b_stage_bytes;
-  s.bars = s.stage_out + T3_NWG * T3_STAGE_OUT;
+  s.bars = s.stage_out + T3_NWG * t3_stage_out_bytes(gw);
   s.params = s.bars + 512;
   s.scratch = s.params + 20 * cout_pad;                           // 16 B per channel (pairs) + 4 B bias
-  s.total = s.scratch + T3_NWG * 4 * S_t * (ng > 0 ? ng : 1) * 8 + 1024 /*alignment slack*/;
+  s.total = s.scratch + T3_NWG * 4 * S_t * ng * 8 + 1024 /*alignment slack*/;
   return s;
 }
 
@@ -135,8 +139,12 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   constexpr int BN_ITEM = NS * T3_BN;                     // output channels per work item
   constexpr int ACC = 512 / BN_ITEM;                      // TMEM accumulator stages
   constexpr int CW = 16;                                  // columns per TMEM load
-  constexpr int NCHUNK = T3_BN / CW;
-  constexpr int NG = (GW > 0) ? T3_BN / GW : 1;           // GroupNorm groups per 128-column sub-tile
+  constexpr int UC = t3_unit_cols(GW);                    // columns per epilogue unit
+  constexpr int UPI = BN_ITEM / UC;                       // units per whole item
+  constexpr int UPH = (UPI > 1) ? UPI / 2 : 1;            // units per half entry (256-wide items only)
+  constexpr int STAGE_OUT = t3_stage_out_bytes(GW);
+  constexpr int NCHUNK = UC / CW;
+  constexpr int NG = (GW > 0) ? UC / GW : 1;              // GroupNorm groups per unit
   constexpr int GPC = (GW > 0 && GW < CW) ? CW / GW : 1;  // groups per column chunk
   constexpr int CPG = (GW >= CW) ? GW / CW : 1;           // chunks per group
   constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1u);
@@ -145,7 +153,7 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int n_tiles_n = p.n_tiles_n;                      // items along N (BN_ITEM wide)
   const int cout_pad = n_tiles_n * BN_ITEM;
-  const T3Smem lay = t3_smem_layout(p.a_stage_bytes, p.n_a_stages, p.b_stage_bytes, cout_pad, p.S_t, NG);
+  const T3Smem lay = t3_smem_layout(p.a_stage_bytes, p.n_a_stages, p.b_stage_bytes, cout_pad, p.S_t, GW);
   const uint32_t s_base = ptx::smem_u32(smem);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + lay.bars);
   uint64_t *full_a = bars;                 // [4]
@@ -215,7 +223,7 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     for (int s = 0; s < 2 * T3_NWG; ++s) ptx::mbar_init(&ufull[s], 1);
     for (int s = 0; s < ACC; ++s) {
       // every 128-column unit of the item is drained by 4 warps; pair: the epilogue warps of both CTAs
-      ptx::mbar_init(&tempty[s], (MODE == T3_PAIR ? 8 : 4) * NS);
+      ptx::mbar_init(&tempty[s], (MODE == T3_PAIR ? 8 : 4) * UPI);
     }
     for (int s = 0; s < T3_NWG; ++s) ptx::mbar_init(&res_bar[s], 1);
     ptx::fence_barrier_init();
@@ -389,10 +397,10 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         }
         if (leader_lane) {
           // units of this entry: NS for a whole item, one for a half entry (numbered after all whole items)
-          const int u0 = half ? NS * full_rounds + (it - full_rounds) : it * NS;
+          const int u0 = half ? UPI * full_rounds + (it - full_rounds) * UPH : it * UPI;
 #pragma unroll
-          for (int ns = 0; ns < NS; ++ns) {
-            if (half && ns > 0) break;
+          for (int ns = 0; ns < UPI; ++ns) {
+            if (half && ns >= UPH) break;
             const int u = u0 + ns, k = u / T3_NWG;
             uint64_t *bar = &ufull[(u - k * T3_NWG) * 2 + (k & 1)];
             if constexpr (MODE == T3_PAIR) ptx::umma_commit_2sm_mc(bar, MC_MASK);
@@ -412,8 +420,8 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     const int pos_per_half = 128 / p.S_t;
     const bool elected = (threadIdx.x - 64) % 128 == 0;
     const float inv_n = 1.0f / (float)(p.L * (GW > 0 ? GW : 1));
-    uint8_t *stg_ptr = smem + lay.stage_out + wg * T3_STAGE_OUT;
-    const uint32_t stg = s_base + lay.stage_out + wg * T3_STAGE_OUT;         // [2 boxes][128 rows][128 B], swizzled
+    uint8_t *stg_ptr = smem + lay.stage_out + wg * STAGE_OUT;
+    const uint32_t stg = s_base + lay.stage_out + wg * STAGE_OUT;            // [UC/64 boxes][128 rows][128 B], swizzled
     const uint32_t scr = s_scr + (uint32_t)wg * (4u * p.S_t * NG * 8u);      // [4 warps][S_t][NG] x (sum, sumsq)
     const uint32_t row_off = (uint32_t)r * 128u;
     const uint32_t swz = (uint32_t)(r & 7);
@@ -424,31 +432,36 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     // Residual tiles travel through the staging buffer: the box for unit (item, ns, h) is requested as soon as
     // the previous unit's store has finished reading the buffer.
     // unit u -> (entry index, item, 128-column sub-tile, half entry?)
-    auto unit = [&](int u, int &j, int &item, int &ns, bool &half) -> bool {
+    // `ns` = column block (UC wide) of the item the unit covers, `acol` = its column offset inside the accumulator
+    auto unit = [&](int u, int &j, int &item, int &ns, int &acol, bool &half) -> bool {
       int ns_only;
-      if (u < NS * full_rounds) {
-        j = u / NS;
-        ns = u - j * NS;
+      if (u < UPI * full_rounds) {
+        j = u / UPI;
+        ns = u - j * UPI;
+        acol = ns * UC;
         return entry(j, item, half, ns_only);
       }
-      j = full_rounds + (u - NS * full_rounds);
+      const int v = u - UPI * full_rounds;
+      j = full_rounds + v / UPH;
+      const int s2 = v - (v / UPH) * UPH;
       const bool ok = entry(j, item, half, ns_only);
-      ns = ns_only;
+      ns = ns_only * UPH + s2;
+      acol = s2 * UC;                       // a half entry accumulates in the first 128 columns of its stage
       return ok;
     };
     auto request_residual = [&](int item, int ns, int h) {
       const int gm = item / n_tiles_n, tn = item - gm * n_tiles_n;
       const int tm = gm * CL + (int)cta_rank;
-      const int ch0 = tn * BN_ITEM + ns * T3_BN;
-      ptx::mbar_arrive_expect_tx(&res_bar[wg], T3_STAGE_OUT);
+      const int ch0 = tn * BN_ITEM + ns * UC;
+      ptx::mbar_arrive_expect_tx(&res_bar[wg], STAGE_OUT);
       ptx::tma_load_3d(stg_ptr, &tmR, &res_bar[wg], ch0, tm * p.S_t, h * pos_per_half);
-      ptx::tma_load_3d(stg_ptr + 16384, &tmR, &res_bar[wg], ch0 + 64, tm * p.S_t, h * pos_per_half);
+      if constexpr (UC == 128) ptx::tma_load_3d(stg_ptr + 16384, &tmR, &res_bar[wg], ch0 + 64, tm * p.S_t, h * pos_per_half);
     };
     auto release_acc = [&](int as, bool twice) {
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        // a half entry has one unit where the barrier expects NS: arrive for the missing one too
+        // a half entry has half the units the barrier expects: arrive for the missing ones too
         for (int rep = 0; rep < (twice ? 2 : 1); ++rep) {
           if constexpr (MODE == T3_PAIR) ptx::mbar_arrive_cluster(tempty0 + 8u * as);
           else ptx::mbar_arrive(&tempty[as]);
@@ -458,23 +471,23 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 
     // units: u = it * NS + ns (one 128-column sub-tile of work item `it`, all MH halves); warpgroup wg takes u = wg (mod NWG)
     if (p.has_res && elected) {
-      int j0, item0, ns0;
+      int j0, item0, ns0, ac0;
       bool half0;
-      if (unit(wg, j0, item0, ns0, half0)) request_residual(item0, ns0, 0);
+      if (unit(wg, j0, item0, ns0, ac0, half0)) request_residual(item0, ns0, 0);
     }
 
     for (int u = wg;; u += T3_NWG) {
-      int it, item, ns;
+      int it, item, ns, acol;
       bool half;
-      if (!unit(u, it, item, ns, half)) break;
+      if (!unit(u, it, item, ns, acol, half)) break;
       if (p.prof) pc_t0 = clock64();
       const int gm = item / n_tiles_n, tn = item - gm * n_tiles_n;
       const int tm = gm * CL + (int)cta_rank;
       const int b0 = tm * p.S_t;
       const bool tile_ok = tm < p.n_mst;
-      int nit, nitem = total_items, nns = 0;                             // this warpgroup's next unit
+      int nit, nitem = total_items, nns = 0, nacol;                      // this warpgroup's next unit
       bool nhalf;
-      if (!unit(u + T3_NWG, nit, nitem, nns, nhalf)) nitem = total_items;
+      if (!unit(u + T3_NWG, nit, nitem, nns, nacol, nhalf)) nitem = total_items;
       const bool twice = half && NS == 2;
       uint32_t t_addr[MH];
       {
@@ -496,8 +509,8 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       }
 
       {
-        const int n0 = tn * BN_ITEM + ns * T3_BN;
-        const uint32_t col0 = half ? 0u : (uint32_t)(ns * T3_BN);      // a half entry accumulates in the first 128 columns
+        const int n0 = tn * BN_ITEM + ns * UC;
+        const uint32_t col0 = (uint32_t)acol;
         if constexpr (GW > 0) {
           // ---- pass 1: GroupNorm statistics of (conv + bias) over the L positions x GW channels of each sample.
           // This thread's rows (one per half) belong to ONE sample; lanes with equal (lane % S_t) share it.
@@ -650,7 +663,7 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           if (elected) {
             if (!(p.debug & 4)) {
               ptx::tma_store_3d(&tmO, stg, n0, b0, h * pos_per_half);
-              ptx::tma_store_3d(&tmO, stg + 16384, n0 + 64, b0, h * pos_per_half);
+              if constexpr (UC == 128) ptx::tma_store_3d(&tmO, stg + 16384, n0 + 64, b0, h * pos_per_half);
             }
             ptx::bulk_commit();
             if (p.has_res && nx_item < total_items) {

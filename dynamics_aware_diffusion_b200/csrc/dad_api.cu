@@ -506,10 +506,9 @@ int setup_t3_op(dad_handle *h, ConvOp &op) {
   op.t3_NS = (op.t3_mode == T3_PAIR && op.t3_MH == 1 && g.Cout % 256 == 0 && want_ns == 2) ? 2 : 1;
   p.n_tiles_n = g.Cout / (T3_BN * op.t3_NS);
   p.b_stage_bytes = op.t3_mode == T3_PAIR ? op.t3_NS * 8192 : 16384;
-  const int ng = op.GW > 0 ? T3_BN / op.GW : 1;
   int na = 4;
   for (; na >= 2; --na) {
-    op.t3_smem = t3_smem_layout(p.a_stage_bytes, na, p.b_stage_bytes, g.Cout, S_t, ng).total;
+    op.t3_smem = t3_smem_layout(p.a_stage_bytes, na, p.b_stage_bytes, g.Cout, S_t, op.GW).total;
     if (op.t3_smem <= h->max_smem_optin) break;
   }
   if (na < 2) return DAD_ERR_INVALID;     // caller falls back to the generic path
