@@ -26,7 +26,10 @@ namespace dad {
 
 constexpr int T3_BN = 128;
 constexpr int T3_BK = 64;
-constexpr int T3_NB = 4;            // weight-tile ring
+#ifndef DAD_T3_NB
+#define DAD_T3_NB 6
+#endif
+constexpr int T3_NB = DAD_T3_NB;    // weight-tile ring (<= 8)
 #ifndef DAD_T3_NWG
 #define DAD_T3_NWG 3
 #endif
@@ -158,16 +161,16 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + lay.bars);
   uint64_t *full_a = bars;                 // [4]
   uint64_t *empty_a = bars + 4;            // [4]
-  uint64_t *full_b = bars + 8;             // [T3_NB]
-  uint64_t *empty_b = bars + 12;           // [T3_NB]
-  uint64_t *tempty = bars + 16;            // [ACC]
-  uint64_t *res_bar = bars + 20;           // [T3_NWG] (<= 4)
+  uint64_t *full_b = bars + 8;             // [T3_NB] (<= 8)
+  uint64_t *empty_b = bars + 16;           // [T3_NB]
+  uint64_t *tempty = bars + 24;            // [ACC]
+  uint64_t *res_bar = bars + 28;           // [T3_NWG] (<= 4)
   // "accumulator ready" is signalled PER CONSUMER: unit u (the k-th unit of warpgroup w = u % NWG, k = u / NWG)
   // completes ufull[w][k & 1].  Every barrier is then waited on in strictly consecutive phases by one warpgroup;
   // a per-accumulator-stage barrier would be revisited by a warpgroup only every few phases and its parity
   // test would alias.
-  uint64_t *ufull = bars + 24;             // [T3_NWG][2]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 32);
+  uint64_t *ufull = bars + 32;             // [T3_NWG][2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 40);
   const uint32_t s_pair = s_base + lay.params;                      // [cout_pad/2] x {g0,g1,b0,b1 | bias0,bias1,t0,t1}
   const uint32_t s_bias = s_pair + 16u * (uint32_t)cout_pad;        // [cout_pad] floats
   const uint32_t s_scr = s_base + lay.scratch;
