@@ -372,6 +372,20 @@ def main():
         except Exception as exc:      # measurement extra: never fail the bench line over it
             line["roofline_step_kernel_stream"] = {"error": str(exc)[:200]}
         line["unet_ms_sum_of_layers"] = unet_ms
+        # the production caller's shape (GuidedPolicy.get_action, policies.py:193-223): ONE plan, latency-bound
+        try:
+            lat = []
+            for k in range(4):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                one = pol.sample_loop(batch_size=1, conditions={0: start}, seed=k)
+                _ = one[0, :2].cpu()                      # the actions get_action reads back
+                lat.append((time.perf_counter() - t0) * 1e3)
+            line["plan_latency_b1_ms"] = {"p50": statistics.median(lat[1:]), "diffusion_steps": S,
+                                          "note": "sample_loop(batch_size=1) + D2H of the first actions, wall clock"}
+            eng.set_conditions({0: start}, B)
+        except Exception as exc:
+            line["plan_latency_b1_ms"] = {"error": str(exc)[:200]}
         if args.layers_out:
             os.makedirs(os.path.dirname(os.path.abspath(args.layers_out)), exist_ok=True)
             json.dump(table, open(args.layers_out, "w"), indent=1)
