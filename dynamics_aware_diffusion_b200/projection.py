@@ -105,6 +105,18 @@ def fold_projection(P, obs_mean, obs_std, action_mean, action_std, state_dim, ac
     return M - np.eye(H * T), q
 
 
+def dynamics_residual(x, P, obs_mean, obs_std, action_mean, action_std, state_dim, action_dim):
+    """mean((tau - tau P)^2) in physical space for normalised trajectories x (B, H, T): the reference's dynamics
+    violation metric, ProjectionLoss.compute (m_diffuser/losses/__init__.py:161-186), numpy fp64."""
+    x = np.asarray(x, dtype=np.float64)
+    B = x.shape[0]
+    s = x[:, :, :state_dim] * np.asarray(obs_std, np.float64) + np.asarray(obs_mean, np.float64)
+    a = x[:, :, state_dim:state_dim + action_dim] * np.asarray(action_std, np.float64) + np.asarray(action_mean, np.float64)
+    s = np.concatenate([s, s[:, -1:, :]], axis=1)                       # duplicated last state (losses/__init__.py:153)
+    c = np.concatenate([s.reshape(B, -1), a.reshape(B, -1)], axis=1)
+    return float(np.mean((c - c @ np.asarray(P, dtype=np.float64)) ** 2))
+
+
 def projection_alphas(n_table, n_timesteps, schedule, strength, betas=None):
     """alpha_i for i in [0, n_table): policies.py:358-383 (progress = i / n_timesteps)."""
     i = np.arange(n_table, dtype=np.float64)

@@ -165,3 +165,43 @@ def test_product_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+
+
+@pytest.mark.parametrize("name", ["pointmaze", "cheetah_s", "door_s"])
+def test_checkpoint_arch_inference(name, tmp_path):
+    """infer_model_config_from_checkpoint (evaluate.py:64-122) incl. the (1,4,8) case the reference mis-infers, and
+    load_diffusion round-tripping a training checkpoint (utils/training.py:193-211) with optional EMA weights."""
+    from dynamics_aware_diffusion_b200 import infer_model_config_from_checkpoint, load_diffusion
+    c = helpers.CASES[name]
+    sd, dif = helpers.make_state_dict(c)
+    ema = {k: v.clone() + 0.5 for k, v in dif.named_parameters()}
+    ckpt = {"epoch": 1, "global_step": 5, "model_state_dict": dif.state_dict(), "ema_state_dict": ema,
+            "config": {"horizon": c["H"], "observation_dim": c["n"], "action_dim": c["m"], "n_timesteps": c["S"],
+                       "beta_schedule": c["beta"]}}
+    cfg = infer_model_config_from_checkpoint(ckpt)
+    assert cfg["dim"] == c["dim"] and tuple(cfg["dim_mults"]) == tuple(c["mults"]) and cfg["n_timesteps"] == c["S"]
+    assert cfg["horizon"] == c["H"] and cfg["beta_schedule"] == c["beta"] and cfg["transition_dim"] == c["n"] + c["m"]
+    path = tmp_path / "checkpoint_best.pt"
+    torch.save(ckpt, path)
+    model, _ = load_diffusion(str(path), device="cpu")
+    for k, v in model.state_dict().items():
+        assert np.array_equal(v.numpy(), sd[k]), k
+    model_ema, _ = load_diffusion(ckpt, device="cpu", use_ema=True)
+    k0 = "model.time_mlp.1.weight"
+    assert np.allclose(model_ema.state_dict()[k0].numpy(), sd[k0] + 0.5)
+    with pytest.raises(ValueError):
+        load_diffusion(ckpt, observation_dim=c["n"] + 1, action_dim=c["m"], device="cpu")
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_dynamics_residual_matches_reference(name):
+    """dynamics_residual == ProjectionLoss.compute on the reference's own trajectories (golden residual_dyn)."""
+    from dynamics_aware_diffusion_b200 import dynamics_residual
+    c = helpers.CASES[name]
+    g = helpers.load_golden(name)
+    P = g["P"] if "P" in g else ProjectionMatrixBuilder(g["A"], g["Bm"], c["n"], c["m"]).get_projection_matrix(c["H"]).numpy()
+    nz = helpers.normalizer(c)
+    for k in (0, c["S"] - 1):
+        got = dynamics_residual(g["trace_dyn"][k], P, nz.obs_mean, nz.obs_std, nz.action_mean, nz.action_std, c["n"], c["m"])
+        want = float(g["residual_dyn"][k])
+        assert abs(got - want) <= 1e-4 * max(want, 1e-3)
