@@ -117,8 +117,9 @@ def projector_inputs(w):
     return ProjectionMatrixBuilder(A, B, w["n"], w["m"]).get_projection_matrix(w["H"]), nz
 
 
-def stream_step_roofline(dev, pk, B=65536, H=32, T=6):
-    """K7 (x0, clamp, posterior mean, Philox noise, inpainting; no projector) at B=65536: 12*H*T*B = 151 MB per launch."""
+def stream_step_roofline(dev, pk, B=262144, H=32, T=6):
+    """K7 (x0, clamp, posterior mean, noise, inpainting; no projector) at B=262144: 12*H*T*B = 604 MB per launch with
+    in-kernel Philox, 805 MB with injected noise -- several times the 126 MB L2, so every byte comes from HBM."""
     import torch
     from dynamics_aware_diffusion_b200 import TemporalUnet, GaussianDiffusion, _native as N
     net = TemporalUnet(T, dim=64, dim_mults=(1,), precision="fp32", max_batch=B)      # small arena; the U-Net is not run

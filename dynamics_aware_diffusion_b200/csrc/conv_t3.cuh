@@ -26,6 +26,9 @@ namespace dad {
 
 constexpr int T3_BN = 128;
 constexpr int T3_BK = 64;
+#ifndef DAD_T3_CW
+#define DAD_T3_CW 16
+#endif
 #ifndef DAD_T3_NB
 #define DAD_T3_NB 6
 #endif
@@ -141,7 +144,7 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   constexpr int CL = (MODE == T3_SINGLE) ? 1 : 2;
   constexpr int BN_ITEM = NS * T3_BN;                     // output channels per work item
   constexpr int ACC = 512 / BN_ITEM;                      // TMEM accumulator stages
-  constexpr int CW = 16;                                  // columns per TMEM load
+  constexpr int CW = DAD_T3_CW;                           // columns per TMEM load / epilogue chunk (8 or 16)
   constexpr int UC = t3_unit_cols(GW);                    // columns per epilogue unit
   constexpr int UPI = BN_ITEM / UC;                       // units per whole item
   constexpr int UPH = (UPI > 1) ? UPI / 2 : 1;            // units per half entry (256-wide items only)
@@ -534,7 +537,7 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll
             for (int h = 0; h < MH; ++h) {
               uint32_t v[32];
-              ptx::tmem_ld16(t_addr[h] + col0 + c * CW, v);
+              if constexpr (CW == 16) ptx::tmem_ld16(t_addr[h] + col0 + c * CW, v); else ptx::tmem_ld8(t_addr[h] + col0 + c * CW, v);
               ptx::tmem_ld_wait();
 #pragma unroll
               for (int j = 0; j < CW / 2; ++j) {
@@ -582,7 +585,7 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll 1
           for (int c = 0; c < NCHUNK; ++c) {
             uint32_t v[32];
-            ptx::tmem_ld16(t_addr[h] + col0 + c * CW, v);
+            if constexpr (CW == 16) ptx::tmem_ld16(t_addr[h] + col0 + c * CW, v); else ptx::tmem_ld8(t_addr[h] + col0 + c * CW, v);
             const int nc = n0 + c * CW;
             const uint32_t sp = s_pair + (uint32_t)(nc >> 1) * 32u;
             f32x2 y[CW / 2];
@@ -633,26 +636,28 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               for (int j = 0; j < CW / 2; ++j)
                 y[j] = fadd2(pk2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bb[j]);
             }
-            // this thread's 16 columns = two 16-byte pieces of its row in the swizzled staging box
+            // this thread's CW columns = CW/8 16-byte pieces of its row in the swizzled staging box
             const uint32_t box = stg + (uint32_t)((c * CW) >> 6) * 16384u + row_off;
             const uint32_t pc0 = (uint32_t)(((c * CW) & 63) >> 3);
-            const uint32_t ad0 = box + (((pc0) ^ swz) << 4), ad1 = box + (((pc0 + 1) ^ swz) << 4);
-            if (p.has_res) {
-              const uint4 r0 = ptx::lds128u(ad0), r1 = ptx::lds128u(ad1);
-              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-              for (int j = 0; j < CW / 2; ++j)
-                y[j] = fadd2(y[j], pk2(__uint_as_float(rw[j] << 16), __uint_as_float(rw[j] & 0xffff0000u)));
-            }
-            uint32_t ow[CW / 2];
+            for (int pc = 0; pc < CW / 8; ++pc) {
+              const uint32_t ad = box + (((pc0 + pc) ^ swz) << 4);
+              if (p.has_res) {
+                const uint4 r0 = ptx::lds128u(ad);
+                const uint32_t rw[4] = {r0.x, r0.y, r0.z, r0.w};
 #pragma unroll
-            for (int j = 0; j < CW / 2; ++j) {
-              float lo, hi;
-              upk2(y[j], lo, hi);
-              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(ow[j]) : "f"(hi), "f"(lo));
+                for (int j = 0; j < 4; ++j)
+                  y[4 * pc + j] = fadd2(y[4 * pc + j], pk2(__uint_as_float(rw[j] << 16), __uint_as_float(rw[j] & 0xffff0000u)));
+              }
+              uint32_t ow[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float lo, hi;
+                upk2(y[4 * pc + j], lo, hi);
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(ow[j]) : "f"(hi), "f"(lo));
+              }
+              ptx::sts128u(ad, make_uint4(ow[0], ow[1], ow[2], ow[3]));
             }
-            ptx::sts128u(ad0, make_uint4(ow[0], ow[1], ow[2], ow[3]));
-            ptx::sts128u(ad1, make_uint4(ow[4], ow[5], ow[6], ow[7]));
           }
           // this unit no longer needs accumulator h (the barrier counts all units of the item)
           release_acc((it * MH + h) % ACC, twice);

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <climits>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -18,6 +19,8 @@
 #include "conv_t3.cuh"
 #include "kernels_f32.cuh"
 #include "step_kernel.cuh"
+
+#define STEP_FOR_EACH_SPT(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
 
 using namespace dad;
 
@@ -77,6 +80,7 @@ struct dad_handle {
   dad_config cfg{};
   std::string err;
   int sm_count = 0;
+  int step_ctas_per_sm = 8;   // resident step_pointwise_kernel CTAs per SM (occupancy query)
   int max_smem_optin = 0;
   bool bf16 = false;
   int time_dim = 0, D = 0, Cpad_in = 0;
@@ -611,8 +615,17 @@ int set_kernel_attrs(dad_handle *h) {
 #define T3_ATTR(gw, mh, mode, ns) CK(h, (set_t3_attr<gw, mh, mode, ns>(h->max_smem_optin)));
   T3_FOR_EACH(T3_ATTR)
 #undef T3_ATTR
-  CK(h, cudaFuncSetAttribute(step_project_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+#define STEP_ATTR(spt) CK(h, cudaFuncSetAttribute(step_project_fused_kernel<spt>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  STEP_FOR_EACH_SPT(STEP_ATTR)
+#undef STEP_ATTR
+  CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->step_ctas_per_sm, step_pointwise_kernel, 256, 0));
+  if (h->step_ctas_per_sm < 1) h->step_ctas_per_sm = 1;
   return DAD_OK;
+}
+
+static bool step_fused_fits(const dad_handle *h) {
+  return step_fused_smem(h->D) <= (size_t)h->max_smem_optin && step_fused_threads(h->D) <= STEP_FUSED_MAX_THREADS &&
+         h->D % 4 == 0;
 }
 
 int enqueue_tc(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
@@ -735,18 +748,19 @@ int enqueue_step(dad_handle *h, const float *model_out, int B, bool project, boo
   p.predict_epsilon = c.predict_epsilon;
   p.clip_denoised = c.clip_denoised;
   const size_t total4 = (size_t)B * h->D / 4;
+  if (total4 >= (size_t)1 << 31) DAD_FAIL(h, DAD_ERR_INVALID, "step kernel: B*H*T/4 must be below 2^31");
   if (!project) {
     p.to_tmp = 0;
-    const int grid = (int)std::min<size_t>(cdiv(total4, 256), (size_t)h->sm_count * 8);
+    const int grid = (int)std::min<size_t>(cdiv(total4, 256), (size_t)h->sm_count * h->step_ctas_per_sm);
     launch_k(step_pointwise_kernel, dim3(grid), dim3(256), 0, st, 1, p);
     h->counting += 1;
-  } else if (h->proj_tc && ((size_t)h->D * h->D + (size_t)h->D * STEP_SB + h->D) * sizeof(float) > (size_t)h->max_smem_optin) {
+  } else if (h->proj_tc && !step_fused_fits(h)) {
     // large D (the projector does not fit shared memory): pointwise part -> x' (fp32) + its bf16 (hi | lo | hi) split; then one tcgen05 GEMM against (N_hi | N_hi | N_lo)
     // whose epilogue blends, inpaints and writes x (K8)
     p.to_tmp = 1;
     p.split = h->d_split;
     p.Kp = h->projKp;
-    const int grid = (int)std::min<size_t>(cdiv(total4, 256), (size_t)h->sm_count * 8);
+    const int grid = (int)std::min<size_t>(cdiv(total4, 256), (size_t)h->sm_count * h->step_ctas_per_sm);
     launch_k(step_pointwise_kernel, dim3(grid), dim3(256), 0, st, 1, p);
     ConvTcParams t{};
     t.bias = h->d_qpad;
@@ -771,16 +785,27 @@ int enqueue_step(dad_handle *h, const float *model_out, int B, bool project, boo
              (size_t)TcCfg<128>::smem_bytes(h->projNp), st, 1, h->tmProjA, h->tmProjA, h->tmProjW, t);
     h->counting += 2;
   } else {
-    const size_t fused_smem = ((size_t)h->D * h->D + (size_t)h->D * STEP_SB + h->D) * sizeof(float);
-    if (fused_smem <= (size_t)h->max_smem_optin) {
-      const int grid = std::min(cdiv(B, STEP_SB), h->sm_count);
-      launch_k(step_project_fused_kernel, dim3(grid), dim3(256), fused_smem, st, 1, p);
+    if (step_fused_fits(h)) {
+      // samples per thread: whole rounds of 4*SPT-sample groups over the SMs, least (rounds x SPT); ties -> larger SPT
+      int spt = 8, best = INT_MAX;
+      for (int c = 8; c >= 1; --c) {
+        const int cost = cdiv(cdiv(B, 4 * c), h->sm_count) * c;
+        if (cost < best) { best = cost; spt = c; }
+      }
+      const int grid = std::min(cdiv(B, 4 * spt), h->sm_count);
+      const dim3 blk(step_fused_threads(h->D));
+      const size_t smem = step_fused_smem(h->D);
+      switch (spt) {
+#define STEP_CASE(c) case c: launch_k(step_project_fused_kernel<c>, dim3(grid), blk, smem, st, 1, p); break;
+        STEP_FOR_EACH_SPT(STEP_CASE)
+#undef STEP_CASE
+      }
       h->counting += 1;
     } else {
       // large D: pointwise part to scratch, then the projector as a tiled GEMM whose epilogue
       // blends, inpaints and writes x (K8).
       p.to_tmp = 1;
-      const int grid = (int)std::min<size_t>(cdiv(total4, 256), (size_t)h->sm_count * 8);
+      const int grid = (int)std::min<size_t>(cdiv(total4, 256), (size_t)h->sm_count * h->step_ctas_per_sm);
       launch_k(step_pointwise_kernel, dim3(grid), dim3(256), 0, st, 1, p);
       ConvF32Params g{};
       g.in1 = h->d_xtmp;

@@ -11,6 +11,7 @@
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
+#include "conv_t3.cuh"   // packed fp32x2 helpers
 
 namespace dad {
 
@@ -51,16 +52,20 @@ __device__ __forceinline__ float4 philox_normal4(unsigned quad, unsigned slot, u
                                                  unsigned long long seed) {
   const uint4 r = philox4x32_10(make_uint4(quad, slot, (unsigned)sample, (unsigned)(sample >> 32)),
                                 make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
-  const float k = 2.3283064365386963e-10f;  // 2^-32
-  const float u0 = ((float)r.x + 0.5f) * k, u1 = ((float)r.y + 0.5f) * k;
-  const float u2 = ((float)r.z + 0.5f) * k, u3 = ((float)r.w + 0.5f) * k;
-  float r0, r1;
+  // u in (0, 1): (r + 0.5) 2^-32 as one FMA per draw; lg2 through the raw SFU op (u is never denormal)
+  const float k = 2.3283064365386963e-10f, h = 1.1641532182693481e-10f;   // 2^-32, 2^-33
+  const float u0 = fmaf((float)r.x, k, h), u2 = fmaf((float)r.z, k, h);
+  const float a1 = fmaf((float)r.y, 6.283185307179586f * k, 6.283185307179586f * h);
+  const float a3 = fmaf((float)r.w, 6.283185307179586f * k, 6.283185307179586f * h);
+  float l0, l2, r0, r1;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l0) : "f"(u0));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u2));
   // sqrt(-2 ln u) = sqrt(-2 ln2 * lg2 u)
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(-1.3862943611198906f * __log2f(u0)));
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(-1.3862943611198906f * __log2f(u2)));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(-1.3862943611198906f * l0));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(-1.3862943611198906f * l2));
   float s0, c0, s1, c1;
-  __sincosf(6.283185307179586f * u1, &s0, &c0);
-  __sincosf(6.283185307179586f * u3, &s1, &c1);
+  __sincosf(a1, &s0, &c0);
+  __sincosf(a3, &s1, &c1);
   return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
 }
 
@@ -94,182 +99,276 @@ __global__ void __launch_bounds__(256) init_x_kernel(const LoopState *lsp, const
   *reinterpret_cast<float4 *>(ls.x + e) = make_float4(vv[0], vv[1], vv[2], vv[3]);
 }
 
-// The pointwise part for 4 consecutive elements of sample b starting at d0.
-__device__ __forceinline__ void step_pointwise4(const StepParams &p, const LoopState &ls, int b, int d0,
-                                                float cr, float crm1, float c1, float c2, float sig,
-                                                float gvar, float out[4]) {
-  const size_t e = (size_t)b * p.D + d0;
-  const float4 x4 = *reinterpret_cast<const float4 *>(ls.x + e);
-  const float4 m4 = __ldg(reinterpret_cast<const float4 *>(p.model_out + e));
-  const float xv[4] = {x4.x, x4.y, x4.z, x4.w}, mv[4] = {m4.x, m4.y, m4.z, m4.w};
+// The scalar part of the loop state a step kernel needs, read once into registers (the condition table stays
+// in global memory: indexing a by-value copy of LoopState would put the whole struct in local memory).
+struct StepView {
+  float *x;
+  const float *noise;           // this step's slot of the injected noise, or nullptr -> Philox
+  const float *grad;
+  float *trace;                 // this step's slot of the trace, or nullptr
+  unsigned long long seed, sample_offset;
+  unsigned flags;
+  int step, n_cond, cond_mul, cond_row;
+  float cr, crm1, c1, c2, sig, gvar;
+};
+
+__device__ __forceinline__ StepView step_view(const StepParams &p) {
+  const LoopState *ls = p.ls;
+  StepView v;
+  const int i = ls->step;
+  v.step = i;
+  v.x = ls->x;
+  const float *nz = ls->noise;
+  v.noise = nz ? nz + (size_t)(ls->n_steps - 1 - i) * ls->noise_stride : nullptr;
+  v.grad = ls->grad;
+  float *tr = ls->trace;
+  v.trace = tr ? tr + (size_t)(ls->n_steps - 1 - i) * ls->trace_stride : nullptr;
+  v.seed = ls->seed;
+  v.sample_offset = ls->sample_offset;
+  v.flags = ls->flags;
+  v.n_cond = (v.flags & 1u) ? ls->n_cond : 0;
+  const int per_batch = ls->cond_per_batch;
+  v.cond_mul = per_batch ? ls->cond_B : 1;
+  v.cond_row = per_batch ? ls->cond_row0 : -1;      // -1: one value row shared by the whole batch
+  v.cr = p.sqrt_recip[i];
+  v.crm1 = p.sqrt_recipm1[i];
+  v.c1 = p.coef1[i];
+  v.c2 = p.coef2[i];
+  const float lv = p.logvar[i];
+  v.sig = (i != 0) ? expf(0.5f * lv) : 0.f;
+  v.gvar = v.grad ? ls->guide_w * expf(lv) : 0.f;
+  return v;
+}
+
+// The loads of one float4 of the pointwise part, issued together so that several quads can be in flight per thread.
+struct StepQuad {
+  float4 x, m, z, g;
+};
+__device__ __forceinline__ void step_load4(const StepParams &p, const StepView &v, size_t e, StepQuad &q) {
+  q.x = *reinterpret_cast<const float4 *>(v.x + e);
+  q.m = __ldg(reinterpret_cast<const float4 *>(p.model_out + e));
+  if (v.sig != 0.f && v.noise) q.z = __ldg(reinterpret_cast<const float4 *>(v.noise + e));
+  if (v.gvar != 0.f) q.g = __ldg(reinterpret_cast<const float4 *>(v.grad + e));
+}
+
+// The pointwise part for 4 consecutive elements of sample b starting at d0 (loads already issued).
+__device__ __forceinline__ void step_math4(const StepParams &p, const StepView &v, int b, int d0, const StepQuad &q,
+                                           float out[4]) {
+  const float xv[4] = {q.x.x, q.x.y, q.x.z, q.x.w}, mv[4] = {q.m.x, q.m.y, q.m.z, q.m.w};
   float zv[4] = {0.f, 0.f, 0.f, 0.f}, gv[4] = {0.f, 0.f, 0.f, 0.f};
-  if (sig != 0.f) {
-    if (ls.noise) {
-      const unsigned slot = (unsigned)(ls.n_steps - 1 - ls.step);
-      const float4 z4 = __ldg(reinterpret_cast<const float4 *>(ls.noise + (size_t)slot * ls.noise_stride + e));
-      zv[0] = z4.x; zv[1] = z4.y; zv[2] = z4.z; zv[3] = z4.w;
-    } else {
-      const float4 z4 = philox_normal4((unsigned)(d0 >> 2), (unsigned)ls.step, ls.sample_offset + b, ls.seed);
-      zv[0] = z4.x; zv[1] = z4.y; zv[2] = z4.z; zv[3] = z4.w;
-    }
+  if (v.sig != 0.f) {
+    const float4 z4 = v.noise ? q.z : philox_normal4((unsigned)(d0 >> 2), (unsigned)v.step, v.sample_offset + b, v.seed);
+    zv[0] = z4.x; zv[1] = z4.y; zv[2] = z4.z; zv[3] = z4.w;
   }
-  if (ls.grad && gvar != 0.f) {
-    const float4 g4 = __ldg(reinterpret_cast<const float4 *>(ls.grad + e));
-    gv[0] = g4.x; gv[1] = g4.y; gv[2] = g4.z; gv[3] = g4.w;
-  }
+  if (v.gvar != 0.f) { gv[0] = q.g.x; gv[1] = q.g.y; gv[2] = q.g.z; gv[3] = q.g.w; }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    float x0 = p.predict_epsilon ? (cr * xv[j] - crm1 * mv[j]) : mv[j];
+    float x0 = p.predict_epsilon ? (v.cr * xv[j] - v.crm1 * mv[j]) : mv[j];
     if (p.clip_denoised) x0 = fminf(fmaxf(x0, -1.f), 1.f);
-    float mu = c1 * x0 + c2 * xv[j];
-    mu += gvar * gv[j];
-    out[j] = mu + sig * zv[j];
+    float mu = v.c1 * x0 + v.c2 * xv[j];
+    mu += v.gvar * gv[j];
+    out[j] = mu + v.sig * zv[j];
   }
 }
 
 // x[:, h] = val for every registered (h, val): element d of the flattened (H*T) sample belongs to condition c
 // iff 0 <= d - h_c*T < T (no division: this runs per element inside a bandwidth-bound kernel).
-__device__ __forceinline__ float cond_override(const LoopState &ls, const float *cond_vals, int n_cond, int b,
-                                               int d, int T, float v) {
+template <int N>
+__device__ __forceinline__ void cond_override(const StepParams &p, const StepView &v, int n_cond, int b, int d0,
+                                              float (&o)[N]) {
   for (int c = 0; c < n_cond; ++c) {
-    const unsigned tt = (unsigned)(d - ls.cond_h[c] * T);
-    if (tt < (unsigned)T)
-      v = cond_vals[((size_t)c * (ls.cond_per_batch ? ls.cond_B : 1) +
-                     (ls.cond_per_batch ? (ls.cond_row0 + b) : 0)) * T + tt];
+    const int base = d0 - __ldg(&p.ls->cond_h[c]) * p.T;
+    if (base + N <= 0 || base >= p.T) continue;
+    const float *row = p.cond_vals + ((size_t)c * v.cond_mul + (v.cond_row >= 0 ? v.cond_row + b : 0)) * p.T;
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if ((unsigned)(base + j) < (unsigned)p.T) o[j] = row[base + j];
   }
-  return v;
 }
 
-// Variant A: no projector in this kernel (guided / plain policies, or a projector GEMM follows).
+// Variant A: no projector in this kernel (guided / plain policies, or a projector GEMM follows).  Grid-stride over
+// float4 quads, STEP_U quads per thread per iteration with all their loads issued before the first use; the grid
+// is the resident CTA count (occupancy query on the host).  A shared-memory ring fed by 1-D bulk copies was
+// measured too (round 1): not faster -- with in-kernel Philox the kernel is bound by instruction issue, with
+// injected noise this version already streams at the measured HBM peak.
+#ifndef DAD_STEP_U
+#define DAD_STEP_U 2
+#endif
+constexpr int STEP_U = DAD_STEP_U;
+
 __global__ void __launch_bounds__(256) step_pointwise_kernel(const StepParams p) {
   ptx::griddep_launch();
   ptx::griddep_wait();
-  const LoopState ls = *p.ls;
-  const int i = ls.step;
-  const float cr = p.sqrt_recip[i], crm1 = p.sqrt_recipm1[i], c1 = p.coef1[i], c2 = p.coef2[i];
-  const float lv = p.logvar[i];
-  const float sig = (i != 0) ? expf(0.5f * lv) : 0.f;
-  const float gvar = ls.grad ? ls.guide_w * expf(lv) : 0.f;
+  const StepView v = step_view(p);
   // when a projector GEMM follows, inpaint here only in the inpaint -> project order
-  const int n_cond = ((ls.flags & 1u) && (!p.to_tmp || (ls.flags & 4u))) ? ls.n_cond : 0;
-  float *dst = p.to_tmp ? p.xtmp : ls.x;
-  float *tr = (!p.to_tmp && ls.trace) ? ls.trace + (size_t)(ls.n_steps - 1 - i) * ls.trace_stride : nullptr;
-  const size_t total4 = (size_t)p.B * p.D / 4;
-  // (sample, offset) of this thread's float4 advance by a fixed stride: one division up front, none in the loop
+  const int n_cond = (!p.to_tmp || (v.flags & 4u)) ? v.n_cond : 0;
+  float *dst = p.to_tmp ? p.xtmp : v.x;
+  float *tr = p.to_tmp ? nullptr : v.trace;
+  // 32-bit quad indices (the host rejects B*D/4 >= 2^31); (sample, offset) of this thread's float4 advance by a
+  // fixed stride: one division up front, none in the loop
+  const unsigned total4 = (unsigned)((size_t)p.B * p.D / 4);
   const unsigned D4 = (unsigned)p.D / 4u;
-  const size_t stride4 = (size_t)gridDim.x * blockDim.x;
-  const unsigned sb = (unsigned)(stride4 / D4), sd = (unsigned)(stride4 - (size_t)sb * D4);
-  size_t q4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned b_u = (unsigned)(q4 / D4), d4 = (unsigned)(q4 - (size_t)b_u * D4);
-  for (; q4 < total4; q4 += stride4, b_u += sb, d4 += sd) {
-    if (d4 >= D4) { d4 -= D4; b_u += 1; }
-    const size_t e = q4 * 4;
-    const int b = (int)b_u;
-    const int d0 = (int)(d4 * 4u);
-    float o[4];
-    step_pointwise4(p, ls, b, d0, cr, crm1, c1, c2, sig, gvar, o);
-    if (n_cond) {
+  const unsigned stride4 = gridDim.x * blockDim.x;
+  const unsigned sb = stride4 / D4, sd = stride4 - sb * D4;
+  unsigned q4 = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned b_u = q4 / D4, d4 = q4 - b_u * D4;
+  // quick reject for inpainting: the first two conditions' element ranges live in registers
+  const unsigned span = (unsigned)p.T + 3u;
+  const int lo0 = n_cond > 0 ? __ldg(&p.ls->cond_h[0]) * p.T : 0, lo1 = n_cond > 1 ? __ldg(&p.ls->cond_h[1]) * p.T : lo0;
+  while (q4 < total4) {
+    StepQuad q[STEP_U];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = cond_override(ls, p.cond_vals, n_cond, b, d0 + j, p.T, o[j]);
-    }
-    const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<float4 *>(dst + e) = o4;
-    if (tr) *reinterpret_cast<float4 *>(tr + e) = o4;
-    if (p.split) {
-      // x' = hi + lo with hi, lo in bf16: three bf16 products recover fp32-level accuracy on the tensor cores
-      __nv_bfloat16 hi[4], lo[4];
+    for (int u = 0; u < STEP_U; ++u)
+      if (q4 + u * stride4 < total4) step_load4(p, v, (size_t)(q4 + u * stride4) * 4, q[u]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        hi[j] = __float2bfloat16_rn(o[j]);
-        lo[j] = __float2bfloat16_rn(o[j] - __bfloat162float(hi[j]));
+    for (int u = 0; u < STEP_U; ++u) {
+      if (q4 < total4) {
+        const size_t e = (size_t)q4 * 4;
+        const int b = (int)b_u;
+        const int d0 = (int)(d4 * 4u);
+        float o[4];
+        step_math4(p, v, b, d0, q[u], o);
+        if (n_cond && ((unsigned)(d0 - lo0 + 3) < span || (unsigned)(d0 - lo1 + 3) < span || n_cond > 2))
+          cond_override<4>(p, v, n_cond, b, d0, o);
+        const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4 *>(dst + e) = o4;
+        if (tr) *reinterpret_cast<float4 *>(tr + e) = o4;
+        if (p.split) {
+          // x' = hi + lo with hi, lo in bf16: three bf16 products recover fp32-level accuracy on the tensor cores
+          __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            hi[j] = __float2bfloat16_rn(o[j]);
+            lo[j] = __float2bfloat16_rn(o[j] - __bfloat162float(hi[j]));
+          }
+          __nv_bfloat16 *row = p.split + (size_t)b * 3 * p.Kp + d0;
+          const uint2 h2 = *reinterpret_cast<const uint2 *>(hi), l2 = *reinterpret_cast<const uint2 *>(lo);
+          *reinterpret_cast<uint2 *>(row) = h2;
+          *reinterpret_cast<uint2 *>(row + p.Kp) = l2;
+          *reinterpret_cast<uint2 *>(row + 2 * p.Kp) = h2;
+        }
       }
-      __nv_bfloat16 *row = p.split + (size_t)b * 3 * p.Kp + d0;
-      const uint2 h2 = *reinterpret_cast<const uint2 *>(hi), l2 = *reinterpret_cast<const uint2 *>(lo);
-      *reinterpret_cast<uint2 *>(row) = h2;
-      *reinterpret_cast<uint2 *>(row + p.Kp) = l2;
-      *reinterpret_cast<uint2 *>(row + 2 * p.Kp) = h2;
+      q4 += stride4;
+      b_u += sb;
+      d4 += sd;
+      if (d4 >= D4) { d4 -= D4; b_u += 1; }
     }
   }
 }
 
 // Variant B: projector fused, for D*D*4 bytes that fit shared memory (PointMaze H=32: D=192).
-// Block = 256 threads; the transposed projector Nt[k][d] is staged in shared memory once per block
-// and reused for every sample group the (persistent) block processes.  Per group of SB samples:
-// phase 1 writes x' (pointwise part) to shared memory with float4 accesses; phase 2 has each thread
-// own one output column d for SB/2 samples and accumulate over k with conflict-free Nt reads and
-// broadcast x' reads.
-constexpr int STEP_SB = 16;
+// Block = 4*D threads (thread = one output column d for one quarter of the CTA's samples); the transposed
+// projector Nt[k][d] is staged in shared memory once per block and reused for every sample group the (persistent)
+// block processes.  A group is 4*SPT samples, SPT chosen by the host so that the groups fill the SMs in whole rounds
+// (B=4096 on 148 SMs: SPT=7 -> 147 groups).  Phase 1 writes x' (pointwise part) to shared memory; phase 2
+// accumulates over k with conflict-free Nt reads, broadcast x' reads and packed fp32x2 FMAs.
+//   xs layout: quarter q, row k -> 8 floats (SPT used) at q*9*D + k*8 + (k>>2)*4  (the 4-float pad every 4 rows
+//   spreads phase 1's stores, which walk k in steps of 4 across a warp, over 8 bank groups)
+constexpr int STEP_FUSED_MAX_THREADS = 896;
+__host__ __device__ constexpr size_t step_fused_smem(int D) {
+  return ((size_t)D * D + (size_t)36 * D + D) * sizeof(float);
+}
+__host__ __device__ constexpr int step_fused_threads(int D) { return (4 * D + 31) / 32 * 32; }
 
-__global__ void __launch_bounds__(256) step_project_fused_kernel(const StepParams p) {
+template <int SPT>
+__global__ void __launch_bounds__(STEP_FUSED_MAX_THREADS) step_project_fused_kernel(const StepParams p) {
   extern __shared__ __align__(16) float smem[];
+  constexpr int SB = 4 * SPT, NP = (SPT + 1) / 2;
   const int D = p.D;
   float *Nt = smem;                 // D * D
-  float *xs = Nt + (size_t)D * D;   // D * STEP_SB, layout xs[k][s]
-  float *qs = xs + (size_t)D * STEP_SB;
+  float *xs = Nt + (size_t)D * D;   // 4 quarters * 9 * D
+  float *qs = xs + (size_t)36 * D;
   ptx::griddep_launch();
   // the projector itself is constant: stage it while the U-Net's last kernel drains
   for (int idx = threadIdx.x * 4; idx < D * D; idx += blockDim.x * 4)
     *reinterpret_cast<float4 *>(Nt + idx) = __ldg(reinterpret_cast<const float4 *>(p.Nt + idx));
   for (int d = threadIdx.x; d < D; d += blockDim.x) qs[d] = p.q[d];
+  for (int idx = threadIdx.x; idx < 36 * D; idx += blockDim.x) xs[idx] = 0.f;
   ptx::griddep_wait();
-  const LoopState ls = *p.ls;
-  const int i = ls.step;
-  const float cr = p.sqrt_recip[i], crm1 = p.sqrt_recipm1[i], c1 = p.coef1[i], c2 = p.coef2[i];
-  const float lv = p.logvar[i];
-  const float sig = (i != 0) ? expf(0.5f * lv) : 0.f;
-  const float gvar = ls.grad ? ls.guide_w * expf(lv) : 0.f;
-  const float alpha = p.alpha_tab[i];
-  const bool inpaint_first = (ls.flags & 4u) != 0;
-  const int n_cond = (ls.flags & 1u) ? ls.n_cond : 0;
-  float *tr = ls.trace ? ls.trace + (size_t)(ls.n_steps - 1 - i) * ls.trace_stride : nullptr;
+  const StepView v = step_view(p);
+  const float alpha = p.alpha_tab[v.step];
+  const bool inpaint_first = (v.flags & 4u) != 0;
+  const int n_cond = v.n_cond;
 
-  const int n_groups = (p.B + STEP_SB - 1) / STEP_SB;
+  const int n_groups = (p.B + SB - 1) / SB;
   const int D4 = D / 4;
+  const int pd = (int)threadIdx.x % D, pq = (int)threadIdx.x / D;   // phase-2 role: column pd, quarter pq (< 4 iff active)
+  // inpainting after the projection: whether column pd is overridden (and by which condition) does not depend on the sample
+  int pc = -1, ptt = 0;
+  if (!inpaint_first)
+    for (int c = 0; c < n_cond; ++c) {
+      const int tt = pd - __ldg(&p.ls->cond_h[c]) * p.T;
+      if ((unsigned)tt < (unsigned)p.T) { pc = c; ptt = tt; }
+    }
   for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-    const int b0 = grp * STEP_SB;
+    const int b0 = grp * SB;
     __syncthreads();   // previous group's phase 2 is done with xs (and Nt/qs are loaded)
-    // phase 1: pointwise part -> xs[k][s]
-    for (int w = threadIdx.x; w < STEP_SB * D4; w += blockDim.x) {
-      const int s = w / D4, d0 = (w - s * D4) * 4;
-      const int b = b0 + s;
-      float o[4] = {0.f, 0.f, 0.f, 0.f};
-      if (b < p.B) {
-        step_pointwise4(p, ls, b, d0, cr, crm1, c1, c2, sig, gvar, o);
-        if (inpaint_first && n_cond) {
+    // phase 1: pointwise part -> xs
+    for (int w0 = threadIdx.x; w0 < SB * D4; w0 += 2 * blockDim.x) {
+      StepQuad q[2];
+      int s[2], d0[2];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = cond_override(ls, p.cond_vals, n_cond, b, d0 + j, p.T, o[j]);
-        }
+      for (int u = 0; u < 2; ++u) {
+        const int w = w0 + u * blockDim.x;
+        s[u] = w / D4;
+        d0[u] = (w - s[u] * D4) * 4;
+        if (w < SB * D4 && b0 + s[u] < p.B) step_load4(p, v, (size_t)(b0 + s[u]) * D + d0[u], q[u]);
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) xs[(d0 + j) * STEP_SB + s] = o[j];
+      for (int u = 0; u < 2; ++u) {
+        const int w = w0 + u * blockDim.x;
+        if (w >= SB * D4) break;
+        const int b = b0 + s[u];
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        if (b < p.B) {
+          step_math4(p, v, b, d0[u], q[u], o);
+          if (inpaint_first && n_cond) cond_override<4>(p, v, n_cond, b, d0[u], o);
+        }
+        const int qq = s[u] / SPT, sl = s[u] - qq * SPT;
+        float *dstq = xs + qq * 9 * D + d0[u] * 9 + sl;     // row(d0 + j) = (d0 + j)*8 + d0
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dstq[j * 8] = o[j];
+      }
     }
     __syncthreads();
     // phase 2: y[s][d] = x'[s][d] + alpha * (sum_k Nt[k][d] x'[s][k] + q[d])
-    for (int w = threadIdx.x; w < 2 * D; w += blockDim.x) {
-      const int d = w % D, half = w / D;     // half selects samples [8*half, 8*half + 8)
-      float acc[8];
+    if (pq < 4) {
+      f32x2 acc[NP];
 #pragma unroll
-      for (int s = 0; s < 8; ++s) acc[s] = 0.f;
-      const float *xk = xs + half * 8;
-#pragma unroll 4
-      for (int k = 0; k < D; ++k) {
-        const float m = Nt[k * D + d];
-        const float4 xa = *reinterpret_cast<const float4 *>(xk + k * STEP_SB);
-        const float4 xb = *reinterpret_cast<const float4 *>(xk + k * STEP_SB + 4);
-        acc[0] = fmaf(m, xa.x, acc[0]); acc[1] = fmaf(m, xa.y, acc[1]);
-        acc[2] = fmaf(m, xa.z, acc[2]); acc[3] = fmaf(m, xa.w, acc[3]);
-        acc[4] = fmaf(m, xb.x, acc[4]); acc[5] = fmaf(m, xb.y, acc[5]);
-        acc[6] = fmaf(m, xb.z, acc[6]); acc[7] = fmaf(m, xb.w, acc[7]);
+      for (int j = 0; j < NP; ++j) acc[j] = pk2(0.f, 0.f);
+      const float *xq = xs + pq * 9 * D;
+      const float *np = Nt + pd;
+#pragma unroll 2
+      for (int k4 = 0; k4 < D4; ++k4) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = k4 * 4 + kk;
+          const float m = np[(size_t)k * D];
+          const f32x2 m2 = pk2(m, m);
+          const float *xr = xq + k4 * 36 + kk * 8;
+          const float4 xa = *reinterpret_cast<const float4 *>(xr);
+          acc[0] = ffma2(m2, pk2(xa.x, xa.y), acc[0]);
+          if (NP > 1) acc[1 % NP] = ffma2(m2, pk2(xa.z, xa.w), acc[1 % NP]);
+          if (NP > 2) {
+            const float4 xb = *reinterpret_cast<const float4 *>(xr + 4);
+            acc[2 % NP] = ffma2(m2, pk2(xb.x, xb.y), acc[2 % NP]);
+            if (NP > 3) acc[3 % NP] = ffma2(m2, pk2(xb.z, xb.w), acc[3 % NP]);
+          }
+        }
       }
-      const float qd = qs[d];
+      float r[2 * NP];
 #pragma unroll
-      for (int s = 0; s < 8; ++s) {
-        const int b = b0 + half * 8 + s;
+      for (int j = 0; j < NP; ++j) upk2(acc[j], r[2 * j], r[2 * j + 1]);
+      const float qd = qs[pd];
+      const float *xd = xq + pd * 8 + (pd >> 2) * 4;
+#pragma unroll
+      for (int s = 0; s < SPT; ++s) {
+        const int b = b0 + pq * SPT + s;
         if (b < p.B) {
-          float v = xs[d * STEP_SB + half * 8 + s] + alpha * (acc[s] + qd);
-          if (!inpaint_first && n_cond) v = cond_override(ls, p.cond_vals, n_cond, b, d, p.T, v);
-          ls.x[(size_t)b * D + d] = v;
-          if (tr) tr[(size_t)b * D + d] = v;
+          float y = xd[s] + alpha * (r[s] + qd);
+          if (pc >= 0) y = p.cond_vals[((size_t)pc * v.cond_mul + (v.cond_row >= 0 ? v.cond_row + b : 0)) * p.T + ptt];
+          v.x[(size_t)b * D + pd] = y;
+          if (v.trace) v.trace[(size_t)b * D + pd] = y;
         }
       }
     }
