@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "conv_tc.cuh"
 #include "conv_t3.cuh"
+#include "conv_small.cuh"
 #include "kernels_f32.cuh"
 #include "step_kernel.cuh"
 
@@ -56,6 +57,10 @@ struct ConvOp {
   int t3_MH = 1, t3_mode = 0, t3_NS = 1, t3_smem = 0;
   CUtensorMap t3A1, t3A2, t3W, t3W2, t3R, t3O;
   ConvT3Params t3p{};
+  // small-batch latency path (conv_small.cuh)
+  bool small = false;
+  int sm_mt = 1, sm_cluster = 1, sm_smem = 0;
+  ConvSmallParams smp{};
 };
 
 struct TimeBlock {
@@ -96,6 +101,7 @@ struct dad_handle {
   float *d_sched[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   bool have_weights = false, have_sched = false;
   bool rows_t = false;               // the forward being enqueued has per-row timesteps
+  int small_max_b = 8;               // batches up to this size take the latency kernels (DAD_SMALL_MAX_B, 0 = never)
   // projector
   float *d_Nt = nullptr, *d_Nrow = nullptr, *d_q = nullptr, *d_alpha = nullptr;
   int projD = 0;
@@ -618,8 +624,64 @@ int set_kernel_attrs(dad_handle *h) {
 #define STEP_ATTR(spt) CK(h, cudaFuncSetAttribute(step_project_fused_kernel<spt>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   STEP_FOR_EACH_SPT(STEP_ATTR)
 #undef STEP_ATTR
+  CK(h, cudaFuncSetAttribute(conv_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  CK(h, cudaFuncSetAttribute(conv_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->step_ctas_per_sm, step_pointwise_kernel, 256, 0));
   if (h->step_ctas_per_sm < 1) h->step_ctas_per_sm = 1;
+  return DAD_OK;
+}
+
+// ---- small-batch latency path ---------------------------------------------------------------------
+// Eligible: every bf16-mode layer of at most 32 rows per sample whose weight slab (16 output channels) and haloed
+// activation tile fit shared memory, with GroupNorm groups of 16..128 channels (a cluster of <= 8 CTAs) or none.
+void setup_small_op(dad_handle *h, ConvOp &op) {
+  const ConvGeom &g = op.g;
+  op.small = false;
+  if (!h->bf16 || g.L_out > SM_MAX_L || op.Cout_pad % SM_NCH) return;
+  const int gw = op.gname.empty() ? 0 : g.Cout / kGroups;
+  if (gw && (gw % SM_NCH || gw / SM_NCH > 8)) return;
+  int lo = 0, hi = 0;
+  for (int t = 0; t < g.taps; ++t) { lo = std::min(lo, g.tap_off[t]); hi = std::max(hi, g.tap_off[t]); }
+  ConvSmallParams &p = op.smp;
+  p = ConvSmallParams{};
+  p.halo = -lo;
+  p.rows = p.halo + g.L_in + std::max(0, (g.L_out - 1) * g.in_stride + hi - (g.L_in - 1));
+  op.sm_mt = g.L_out <= 16 ? 1 : 2;
+  op.sm_smem = (int)small_layout(g.C1 + g.C2, g.taps, p.rows, op.sm_mt).total;
+  if (op.sm_smem > h->max_smem_optin) return;
+  op.sm_cluster = gw ? gw / SM_NCH : 1;
+  p.in1 = reinterpret_cast<const __nv_bfloat16 *>(act_ptr(h, op.in1));
+  p.in2 = op.in2 >= 0 ? reinterpret_cast<const __nv_bfloat16 *>(act_ptr(h, op.in2)) : nullptr;
+  p.w = op.w_b16;
+  p.residual = op.tcp.residual;
+  p.bias = op.bias;
+  p.gamma = op.gamma;
+  p.beta = op.beta;
+  p.ttab = op.tcp.ttab;
+  p.out = op.tcp.out;
+  p.ls = h->d_ls;
+  p.C1 = g.C1;
+  p.C2 = g.C2;
+  p.Cout = g.Cout;
+  p.taps = g.taps;
+  for (int t = 0; t < g.taps; ++t) p.tap_off[t] = g.tap_off[t];
+  p.in_stride = g.in_stride;
+  p.L_in = g.L_in;
+  p.L_out = g.L_out;
+  p.out_mul = g.out_mul;
+  p.out_phase = g.out_phase;
+  p.gw = gw;
+  p.out_f32 = op.head ? 1 : 0;
+  op.small = true;
+}
+
+int enqueue_small(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
+  const dim3 grid((unsigned)(op.Cout_pad / SM_NCH), (unsigned)B);
+  const cudaError_t e = op.sm_mt == 1
+      ? launch_k(conv_small_kernel<1>, grid, dim3(SM_THREADS), (size_t)op.sm_smem, st, op.sm_cluster, op.smp)
+      : launch_k(conv_small_kernel<2>, grid, dim3(SM_THREADS), (size_t)op.sm_smem, st, op.sm_cluster, op.smp);
+  if (e != cudaSuccess) DAD_FAIL(h, DAD_ERR_CUDA, "conv_small launch failed for %s: %s", op.wname.c_str(), cudaGetErrorString(e));
+  h->counting += 1;
   return DAD_OK;
 }
 
@@ -629,6 +691,7 @@ static bool step_fused_fits(const dad_handle *h) {
 }
 
 int enqueue_tc(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
+  if (op.small && B <= h->small_max_b && !h->rows_t) return enqueue_small(h, op, B, st);
   if (op.t3 && !h->rows_t) return enqueue_t3(h, op, B, st);      // conv_t3 assumes one timestep for the whole batch
   ConvTcParams p = op.tcp;
   p.B = B;
@@ -1035,7 +1098,9 @@ int dad_create(const dad_config *cfg, dad_handle **out) {
         if ((rc = finish_t3_op(h, op))) return fail(rc);
         op.t3 = true;
       }
+      setup_small_op(h, op);
     }
+  if (getenv("DAD_SMALL_MAX_B")) h->small_max_b = atoi(getenv("DAD_SMALL_MAX_B"));
   if (cudaDeviceSynchronize() != cudaSuccess) { h->err = "device error during create"; return fail(DAD_ERR_CUDA); }
   *out = h;
   return DAD_OK;
@@ -1458,6 +1523,16 @@ int dad_sample_profile(dad_handle *h, float *x, uint64_t seed, uint64_t sample_o
   CK(h, cudaStreamSynchronize(st));
   for (int s = 0; s < n_steps; ++s) CK(h, cudaEventElapsedTime(&step_ms[s], ev[s], ev[s + 1]));
   for (auto &e : ev) cudaEventDestroy(e);
+  return DAD_OK;
+}
+
+int dad_set_latency_batch(dad_handle *h, int32_t max_b) {
+  if (!h || max_b < 0) return DAD_ERR_INVALID;
+  if (max_b != h->small_max_b) {
+    cudaDeviceSynchronize();
+    drop_graphs(h);           // captured steps chose their kernels by batch size
+    h->small_max_b = max_b;
+  }
   return DAD_OK;
 }
 

@@ -218,6 +218,10 @@ class Engine:
     def launch_count(self):
         return int(self.lib.dad_launch_count(self.handle))
 
+    def set_latency_batch(self, max_b):
+        """Batches <= max_b run the latency kernels (get_action's single plan); 0 = throughput kernels only."""
+        self._ck(self.lib.dad_set_latency_batch(self.handle, int(max_b)))
+
 
 def create_engine_auto(precision, **kw):
     """precision 'auto': bf16 tensor-core path when the architecture fits it, else the fp32 CUDA path."""

@@ -58,18 +58,21 @@ class Upsample1d(nn.Module):
 class TemporalUnet(nn.Module):
     """Drop-in for m_diffuser.models.temporal_unet.TemporalUnet (constructor: temporal_unet.py:135-140).
 
-    Extra, optional knobs (not in the reference): `precision` in {'auto','bf16','fp32'} and `max_batch`
-    (workspace capacity in samples; bigger batches are processed in chunks).
+    Extra, optional knobs (not in the reference): `precision` in {'auto','bf16','fp32'}, `max_batch`
+    (workspace capacity in samples; bigger batches are processed in chunks) and `latency_max_batch` (batches up to
+    this size run the latency kernels written for get_action's single plan; None = library default, 0 = never).
     """
 
     def __init__(self, transition_dim: int, dim: int = 128, dim_mults: tuple = (1, 2, 4, 8), kernel_size: int = 5,
-                 time_dim: Optional[int] = None, precision: str = "auto", max_batch: Optional[int] = None):
+                 time_dim: Optional[int] = None, precision: str = "auto", max_batch: Optional[int] = None,
+                 latency_max_batch: Optional[int] = None):
         super().__init__()
         self.transition_dim = transition_dim
         self.dim, self.dim_mults, self.kernel_size = dim, tuple(dim_mults), kernel_size
         self.time_dim = time_dim or dim
         self.precision = os.environ.get("DAD_PRECISION", precision)
         self.max_batch = max_batch or _DEFAULT_MAX_BATCH
+        self.latency_max_batch = latency_max_batch
         td = self.time_dim
         # construction order follows the reference so that default init under a seed is identical
         self.time_mlp = nn.Sequential(SinusoidalPosEmb(dim), nn.Linear(dim, td * 4), nn.Mish(), nn.Linear(td * 4, td))
@@ -114,6 +117,8 @@ class TemporalUnet(nn.Module):
                                      dim_mults=self.dim_mults, kernel_size=self.kernel_size, time_dim=self.time_dim,
                                      horizon=horizon, n_timesteps=n_t, max_batch=self.max_batch, device=device,
                                      **self._diffusion_cfg)
+            if self.latency_max_batch is not None:
+                eng.set_latency_batch(self.latency_max_batch)
             ent = {"engine": eng, "version": None}
             self._engines[key] = ent
         ver = self._weights_version()

@@ -18,7 +18,9 @@ def pointmaze_full():
     from dynamics_aware_diffusion_b200 import TemporalUnet, GaussianDiffusion, DynamicsAwarePolicy, ProjectionMatrixBuilder
     from dynamics_aware_diffusion_b200 import synthetic
     S = 500
-    net = TemporalUnet(6, dim=128, dim_mults=(1, 2, 4), precision="bf16", max_batch=4096)
+    # latency_max_batch=0: every batch size runs the throughput kernels (the row-independence test below compares
+    # small sub-batches with the full batch bit for bit)
+    net = TemporalUnet(6, dim=128, dim_mults=(1, 2, 4), precision="bf16", max_batch=4096, latency_max_batch=0)
     dif = GaussianDiffusion(net, horizon=32, observation_dim=4, action_dim=2, n_timesteps=S)
     synthetic.fill_state_dict(dif, 0)
     dif.to(_dev())
@@ -86,6 +88,40 @@ def test_large_batch_rows_equal_small_batch_rows(pointmaze_full):
     for lo, n in ((0, 64), (1000, 37), (4032, 64), (2047, 2)):
         part = dif.model(x[lo:lo + n].contiguous(), t[:n])
         assert torch.equal(part, full[lo:lo + n]), "rows [%d, %d) depend on the batch they are evaluated in" % (lo, lo + n)
+
+
+@pytest.mark.parametrize("arch", [dict(dim=128, mults=(1, 2, 4), H=32, T=6), dict(dim=64, mults=(1, 4, 8), H=32, T=23),
+                                  dict(dim=64, mults=(1, 2, 4, 8), H=16, T=67)])
+def test_latency_kernels_match_throughput_kernels(arch):
+    """get_action's single-plan shape: the small-batch kernels (conv_small) against the throughput kernels on the
+    same weights and inputs -- same bf16 contract, different summation order -- and row independence within them."""
+    from dynamics_aware_diffusion_b200 import TemporalUnet, GaussianDiffusion, synthetic
+    outs = {}
+    g = torch.Generator(device=_dev()).manual_seed(3)
+    x = torch.randn(8, arch["H"], arch["T"], device=_dev(), generator=g)
+    t = torch.full((8,), 17, device=_dev(), dtype=torch.long)
+    for mode, lat in (("throughput", 0), ("latency", 8)):
+        net = TemporalUnet(arch["T"], dim=arch["dim"], dim_mults=arch["mults"], precision="bf16", max_batch=8,
+                           latency_max_batch=lat)
+        dif = GaussianDiffusion(net, horizon=arch["H"], observation_dim=arch["T"] - 2, action_dim=2, n_timesteps=50)
+        synthetic.fill_state_dict(dif, 0)
+        dif.to(_dev())
+        outs[mode] = dif.model(x, t)
+        if lat:
+            assert torch.equal(dif.model(x, t), outs[mode]), "run-to-run variation in the latency kernels"
+            for lo, n in ((0, 1), (5, 3), (7, 1)):
+                part = dif.model(x[lo:lo + n].contiguous(), t[:n])
+                assert torch.equal(part, outs[mode][lo:lo + n]), "latency kernels: rows depend on the batch"
+            # one whole plan at B = 1, conditions in place (GuidedPolicy.sample_loop, policies.py:114-149)
+            from dynamics_aware_diffusion_b200 import GuidedPolicy
+            pol = GuidedPolicy(dif, synthetic.SyntheticNormalizer(arch["T"] - 2, 2))
+            start = torch.zeros(1, arch["T"], device=_dev())
+            start[0, 0] = 0.25
+            plan = pol.sample_loop(batch_size=1, conditions={0: start}, seed=4)
+            assert plan.shape == (1, arch["H"], arch["T"]) and bool(torch.isfinite(plan).all())
+            assert bool((plan[:, 0] == start).all())
+    err = helpers.rel_l2(outs["latency"].cpu().numpy(), outs["throughput"].cpu().numpy())
+    assert err < 5e-3, err
 
 
 def test_chunking_equals_single_pass():
