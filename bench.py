@@ -135,6 +135,8 @@ def stream_step_roofline(dev, pk, B=262144, H=32, T=6):
         out[key] = {"achieved": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / pk["hbm"],
                     "avg_launch_ms": ms, "bytes_per_launch": nbytes}
     out["achieved"], out["frac"] = out["injected_noise"]["achieved"], out["injected_noise"]["frac"]
+    # DRAM bytes of one injected-noise launch at B=262144 (profiles/r01_ncu_full_stream_b262144.md)
+    out["traffic"] = ncu_traffic("step_pointwise_kernel", "stream_b262144") if B == 262144 else None
     del eng, dif, net
     torch.cuda.empty_cache()
     return out
@@ -364,7 +366,8 @@ def main():
         st_bytes = 12 * H * T * B          # read x, read eps, write x (Philox noise): SURVEY.md 8(d)
         line["roofline_step_kernel"] = {
             "bound": "hbm", "achieved": st_bytes / (st_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-            "frac": st_bytes / (st_ms * 1e-3) / 1e9 / pk["hbm"], "traffic": None, "avg_launch_ms": st_ms,
+            "frac": st_bytes / (st_ms * 1e-3) / 1e9 / pk["hbm"],
+            "traffic": ncu_traffic("step_project_fused_kernel", args.workload), "avg_launch_ms": st_ms,
             "bytes_per_launch": st_bytes, "note": "working set %.1f MB is L2-resident at this B" % (st_bytes / 1e6)}
         # the same memory-bound step kernel without a projector (guided / plain policy) on a batch whose working set
         # leaves the L2 (the HBM fraction is only observable there)
@@ -375,14 +378,21 @@ def main():
         line["unet_ms_sum_of_layers"] = unet_ms
         # the production caller's shape (GuidedPolicy.get_action, policies.py:193-223): ONE plan, latency-bound
         try:
-            lat = []
-            for k in range(4):
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                one = pol.sample_loop(batch_size=1, conditions={0: start}, seed=k)
-                _ = one[0, :2].cpu()                      # the actions get_action reads back
-                lat.append((time.perf_counter() - t0) * 1e3)
-            line["plan_latency_b1_ms"] = {"p50": statistics.median(lat[1:]), "diffusion_steps": S,
+            def one_plan_ms():
+                lat = []
+                for k in range(4):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    one = pol.sample_loop(batch_size=1, conditions={0: start}, seed=k)
+                    _ = one[0, :2].cpu()                      # the actions get_action reads back
+                    lat.append((time.perf_counter() - t0) * 1e3)
+                return statistics.median(lat[1:])
+            p50 = one_plan_ms()                               # default: the latency kernels (conv_small) up to B = 24
+            eng.set_latency_batch(0)
+            p50_tp = one_plan_ms()                            # the same plan through the throughput kernels
+            eng.set_latency_batch(24)
+            line["plan_latency_b1_ms"] = {"p50": p50, "p50_throughput_kernels": p50_tp, "diffusion_steps": S,
+                                          "us_per_diffusion_step": p50 * 1e3 / S,
                                           "note": "sample_loop(batch_size=1) + D2H of the first actions, wall clock"}
             eng.set_conditions({0: start}, B)
         except Exception as exc:

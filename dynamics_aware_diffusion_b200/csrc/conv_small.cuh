@@ -21,10 +21,11 @@
 
 namespace dad {
 
-constexpr int SM_NCH = 16;          // output channels per CTA
-constexpr int SM_THREADS = 256;
-constexpr int SM_WARPS = SM_THREADS / 32;
+constexpr int SM_CONSUMERS = 256;   // 8 MMA / epilogue warps
+constexpr int SM_WARPS = SM_CONSUMERS / 32;
+constexpr int SM_THREADS = SM_CONSUMERS + 32;      // + one producer warp (bulk copies)
 constexpr int SM_MAX_L = 32;        // rows per sample the kernel handles (two m16 tiles)
+constexpr int SM_MAX_STAGES = 4;
 
 struct ConvSmallParams {
   const __nv_bfloat16 *in1, *in2;   // (B, L_in, C1) / (B, L_in, C2) channels-last; in2 = nullptr when C2 == 0
@@ -40,19 +41,21 @@ struct ConvSmallParams {
   int gw;                           // GroupNorm width, 0 = plain convolution
   int out_f32;
   int halo, rows;                   // tile row of input row r is halo + r; rows = tile height
+  int kc, n_stages;                 // weight ring: K elements per chunk (multiple of 16), stages (1 = whole K resident)
 };
 
 struct SmallLayout {
   uint32_t pitch_a, pitch_w, off_w, off_red, off_misc, total;
 };
-__host__ __device__ inline SmallLayout small_layout(int Cin, int taps, int rows, int mt) {
+// mt: m16 tiles per sample, nch: output channels per CTA
+__host__ __device__ inline SmallLayout small_layout(int Cin, int rows, int mt, int nch, int kc, int n_stages) {
   SmallLayout s;
   s.pitch_a = (uint32_t)Cin * 2u + 16u;
-  s.pitch_w = (uint32_t)taps * Cin * 2u + 16u;
+  s.pitch_w = (uint32_t)kc * 2u + 16u;
   s.off_w = (uint32_t)rows * s.pitch_a;
-  s.off_red = s.off_w + SM_NCH * s.pitch_w;
+  s.off_red = s.off_w + (uint32_t)n_stages * nch * s.pitch_w;
   s.off_red = (s.off_red + 15u) & ~15u;
-  s.off_misc = s.off_red + (uint32_t)SM_WARPS * mt * 256u * 4u;      // per warp: mt x (16 x 16) fp32 partials
+  s.off_misc = s.off_red + (uint32_t)SM_WARPS * mt * nch * 16u * 4u;      // per warp: mt x (16 x nch) fp32 partials
   s.total = s.off_misc + 256u;
   return s;
 }
@@ -80,150 +83,211 @@ __device__ __forceinline__ float2 ld_cluster_f32x2(uint32_t cluster_saddr) {
 }
 }  // namespace ptx
 
-// grid = (Cout_pad / 16, B); cluster = (max(1, gw / 16), 1, 1); MT = m16 tiles per sample (1: L_out <= 16, 2: <= 32)
-template <int MT>
+// grid = (Cout_pad / NCH, B); cluster = (max(1, gw / NCH), 1, 1); MT = m16 tiles per sample (1: L_out <= 16,
+// 2: <= 32); NT = n8 tiles per CTA (NCH = 8 NT: 16, or 32 for 256-wide GroupNorm groups so the cluster stays <= 8).
+template <int MT, int NT>
 __global__ void __launch_bounds__(SM_THREADS, 1) conv_small_kernel(const ConvSmallParams p) {
   extern __shared__ __align__(128) unsigned char sm_raw[];
+  constexpr int NCH = 8 * NT;
+  constexpr int NQ = MT * NT * 2;                     // (m tile, n tile, row half) output slices of 32 column pairs
+  constexpr int QI = (NQ + SM_WARPS - 1) / SM_WARPS;  // slices per consumer warp
   const int Cin = p.C1 + p.C2;
   const int K = p.taps * Cin;
-  const SmallLayout lay = small_layout(Cin, p.taps, p.rows, MT);
+  const SmallLayout lay = small_layout(Cin, p.rows, MT, NCH, p.kc, p.n_stages);
   const uint32_t sA = ptx::smem_u32(sm_raw), sW = sA + lay.off_w;
   float *red = reinterpret_cast<float *>(sm_raw + lay.off_red);
-  uint64_t *bar = reinterpret_cast<uint64_t *>(sm_raw + lay.off_misc);      // [0] weights, [1] activations
-  float *stat = reinterpret_cast<float *>(sm_raw + lay.off_misc + 32);       // [0..1] this CTA's (sum, sumsq); [2..17] warp partials
+  uint64_t *full = reinterpret_cast<uint64_t *>(sm_raw + lay.off_misc);     // [stage] weights landed
+  uint64_t *empty = full + SM_MAX_STAGES;                                    // [stage] all consumer warps done
+  uint64_t *abar = empty + SM_MAX_STAGES;                                    // activations landed
+  float *stat = reinterpret_cast<float *>(sm_raw + lay.off_misc + 96);       // [0..1] this CTA's (sum, sumsq); [2..17] warp partials
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n_base = blockIdx.x * SM_NCH, b = blockIdx.y;
+  const int n_base = blockIdx.x * NCH, b = blockIdx.y;
+  const int n_chunks = (K + p.kc - 1) / p.kc;
 
   if (tid == 0) {
-    ptx::mbar_init(&bar[0], 1);
-    ptx::mbar_init(&bar[1], 1);
+    for (int s = 0; s < SM_MAX_STAGES; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], SM_WARPS);
+    }
+    ptx::mbar_init(abar, 1);
     ptx::fence_barrier_init();
   }
   ptx::griddep_launch();
   __syncthreads();
-  // ---- weights: independent of the previous layer, fetched ahead of the dependency wait
-  if (warp == 0) {
-    if (lane == 0) ptx::mbar_arrive_expect_tx(&bar[0], (uint32_t)SM_NCH * K * 2u);
-    __syncwarp();
-    if (lane < SM_NCH)
-      ptx::bulk_load_1d(sW + lane * lay.pitch_w, p.w + (size_t)(n_base + lane) * K, (uint32_t)K * 2u, &bar[0]);
-  }
-  // zero the halo rows (generic stores; nothing else writes them)
-  {
+
+  if (warp == SM_WARPS) {
+    // ---- producer warp.  Weights do not depend on the previous layer: the first n_stages chunks are requested
+    // ahead of the dependency wait; the activations of sample b (one bulk copy per row and source) after it.
+    const int ahead = min(p.n_stages, n_chunks);
+    for (int j = 0; j < ahead; ++j) {
+      const uint32_t bytes = (uint32_t)min(p.kc, K - j * p.kc) * 2u;
+      if (lane == 0) ptx::mbar_arrive_expect_tx(&full[j], (uint32_t)NCH * bytes);
+      __syncwarp();
+      if (lane < NCH)
+        ptx::bulk_load_1d(sW + (uint32_t)(j * NCH + lane) * lay.pitch_w, p.w + (size_t)(n_base + lane) * K + (size_t)j * p.kc,
+                          bytes, &full[j]);
+    }
+    ptx::griddep_wait();
+    {
+      const uint32_t row_bytes = (uint32_t)Cin * 2u;
+      if (lane == 0) ptx::mbar_arrive_expect_tx(abar, (uint32_t)p.L_in * row_bytes);
+      __syncwarp();
+      for (int r = lane; r < p.L_in; r += 32) {
+        const uint32_t dst = sA + (uint32_t)(p.halo + r) * lay.pitch_a;
+        ptx::bulk_load_1d(dst, p.in1 + ((size_t)b * p.L_in + r) * p.C1, (uint32_t)p.C1 * 2u, abar);
+        if (p.C2) ptx::bulk_load_1d(dst + (uint32_t)p.C1 * 2u, p.in2 + ((size_t)b * p.L_in + r) * p.C2, (uint32_t)p.C2 * 2u, abar);
+      }
+    }
+  } else {
+    // zero the halo rows (generic stores; nothing else writes them)
     const int halo_hi = p.rows - p.halo - p.L_in;
     const int vec_per_row = (int)(lay.pitch_a / 16u);
-    for (int i = tid; i < (p.halo + halo_hi) * vec_per_row; i += SM_THREADS) {
+    for (int i = tid; i < (p.halo + halo_hi) * vec_per_row; i += SM_CONSUMERS) {
       const int r = i / vec_per_row, v = i - r * vec_per_row;
       const int row = r < p.halo ? r : p.halo + p.L_in + (r - p.halo);
       *reinterpret_cast<uint4 *>(sm_raw + (size_t)row * lay.pitch_a + v * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
-  }
-  ptx::griddep_wait();
-  // ---- activations of sample b: one bulk copy per (row, source)
-  if (warp == 1) {
-    const uint32_t row_bytes = (uint32_t)Cin * 2u;
-    if (lane == 0) ptx::mbar_arrive_expect_tx(&bar[1], (uint32_t)p.L_in * row_bytes);
-    __syncwarp();
-    for (int r = lane; r < p.L_in; r += 32) {
-      const uint32_t dst = sA + (uint32_t)(p.halo + r) * lay.pitch_a;
-      ptx::bulk_load_1d(dst, p.in1 + ((size_t)b * p.L_in + r) * p.C1, (uint32_t)p.C1 * 2u, &bar[1]);
-      if (p.C2) ptx::bulk_load_1d(dst + (uint32_t)p.C1 * 2u, p.in2 + ((size_t)b * p.L_in + r) * p.C2, (uint32_t)p.C2 * 2u, &bar[1]);
-    }
+    ptx::griddep_wait();
   }
   const int step = p.ls->step;
   __syncthreads();                 // halo rows visible to every warp
-  ptx::mbar_wait(&bar[0], 0);
-  ptx::mbar_wait(&bar[1], 0);
+  if (warp == SM_WARPS) {
+    // refill the ring behind the consumers
+    for (int j = min(p.n_stages, n_chunks); j < n_chunks; ++j) {
+      ptx::mbar_wait(&empty[j % p.n_stages], (uint32_t)((j / p.n_stages - 1) & 1));
+      const int st = j % p.n_stages;
+      const uint32_t bytes = (uint32_t)min(p.kc, K - j * p.kc) * 2u;
+      if (lane == 0) ptx::mbar_arrive_expect_tx(&full[st], (uint32_t)NCH * bytes);
+      __syncwarp();
+      if (lane < NCH)
+        ptx::bulk_load_1d(sW + (uint32_t)(st * NCH + lane) * lay.pitch_w, p.w + (size_t)(n_base + lane) * K + (size_t)j * p.kc,
+                          bytes, &full[st]);
+    }
+    if (p.gw / NCH <= 1) return;      // the producer warp only stays for the cluster barriers
+  }
 
-  // ---- K split over the warps: k16 step s covers tap s / (Cin/16), channels 16 (s % (Cin/16)) ..
-  float acc[MT][2][4];
+  float v0[QI], v1[QI];
+  bool valid[QI], valid1[QI];
+  int row_o[QI], col_o[QI];
+  if (warp < SM_WARPS) {
+    ptx::mbar_wait(abar, 0);
+    // ---- K split over the warps: k16 step s covers tap s / (Cin/16), channels 16 (s % (Cin/16)) ..
+    float acc[MT][NT][4];
 #pragma unroll
-  for (int mt = 0; mt < MT; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
+      for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[mt][nt][j] = 0.f;
-  const int cps = Cin >> 4, n_steps = K >> 4;
-  // ldmatrix row roles of this lane: A matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15); B matrices (n 0-7 | 8-15) x (k 0-7 | 8-15)
-  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_kofs = (lane >> 4) * 8;
-  const int b_row = (lane & 7) + (lane >> 4) * 8, b_kofs = ((lane >> 3) & 1) * 8;
-  int l_of[MT];
+        for (int j = 0; j < 4; ++j) acc[mt][nt][j] = 0.f;
+    const int cps = Cin >> 4, spc = p.kc >> 4;
+    // ldmatrix row roles of this lane: A matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15); B matrices (n 0-7 | 8-15) x (k 0-7 | 8-15)
+    const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_kofs = (lane >> 4) * 8;
+    const int b_row = (lane & 7) + (lane >> 4) * 8, b_kofs = ((lane >> 3) & 1) * 8;
+    int l_of[MT];
 #pragma unroll
-  for (int mt = 0; mt < MT; ++mt) l_of[mt] = min(mt * 16 + a_row, p.L_out - 1);      // padding rows re-read a valid row
-  const uint32_t w_lane = sW + (uint32_t)b_row * lay.pitch_w + (uint32_t)b_kofs * 2u;
-  for (int s = warp; s < n_steps; s += SM_WARPS) {
-    const int t = s / cps, c = (s - t * cps) << 4;
-    uint32_t bf[4];
-    ptx::ldmatrix_x4(w_lane + (uint32_t)s * 32u, bf[0], bf[1], bf[2], bf[3]);
-    const int off = p.tap_off[t] + p.halo;
+    for (int mt = 0; mt < MT; ++mt) l_of[mt] = min(mt * 16 + a_row, p.L_out - 1);      // padding rows re-read a valid row
+    for (int j = 0; j < n_chunks; ++j) {
+      const int st = j % p.n_stages;
+      ptx::mbar_wait(&full[st], (uint32_t)((j / p.n_stages) & 1));
+      const uint32_t w_lane = sW + (uint32_t)(st * NCH + b_row) * lay.pitch_w + (uint32_t)b_kofs * 2u;
+      const int steps = min(p.kc, K - j * p.kc) >> 4;
+      for (int sl = warp; sl < steps; sl += SM_WARPS) {
+        const int s = j * spc + sl;
+        const int t = s / cps, c = (s - t * cps) << 4;
+        uint32_t bf[NT / 2][4];
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      uint32_t af[4];
-      ptx::ldmatrix_x4(sA + (uint32_t)(l_of[mt] * p.in_stride + off) * lay.pitch_a + (uint32_t)(c + a_kofs) * 2u, af[0], af[1],
-                       af[2], af[3]);
-      ptx::mma_bf16_16816(acc[mt][0], af, bf[0], bf[1]);
-      ptx::mma_bf16_16816(acc[mt][1], af, bf[2], bf[3]);
+        for (int h = 0; h < NT / 2; ++h)
+          ptx::ldmatrix_x4(w_lane + (uint32_t)h * 16u * lay.pitch_w + (uint32_t)sl * 32u, bf[h][0], bf[h][1], bf[h][2], bf[h][3]);
+        const int off = p.tap_off[t] + p.halo;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          uint32_t af[4];
+          ptx::ldmatrix_x4(sA + (uint32_t)(l_of[mt] * p.in_stride + off) * lay.pitch_a + (uint32_t)(c + a_kofs) * 2u, af[0], af[1],
+                           af[2], af[3]);
+#pragma unroll
+          for (int h = 0; h < NT / 2; ++h) {
+            ptx::mma_bf16_16816(acc[mt][2 * h], af, bf[h][0], bf[h][1]);
+            ptx::mma_bf16_16816(acc[mt][2 * h + 1], af, bf[h][2], bf[h][3]);
+          }
+        }
+      }
+      if (p.n_stages < n_chunks) {
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty[st]);
+      }
+    }
+    // ---- sum the warps' partial tiles: red[warp][q][lane][2], q = (mt, nt, row half)
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
+          *reinterpret_cast<float2 *>(red + ((warp * NQ + (mt * NT + nt) * 2 + hf) * 32 + lane) * 2) =
+              make_float2(acc[mt][nt][2 * hf], acc[mt][nt][2 * hf + 1]);
+    ptx::named_bar_sync(1, SM_CONSUMERS);
+    // consumer warp -> slices q = warp, warp + 8, ...; thread -> one (row, column pair) of the slice
+#pragma unroll
+    for (int i = 0; i < QI; ++i) {
+      const int q = warp + i * SM_WARPS;
+      const bool has_out = q < NQ;
+      const int mt_o = q / (NT * 2), nt_o = (q >> 1) % NT, hf_o = q & 1;
+      row_o[i] = mt_o * 16 + (lane >> 2) + hf_o * 8;
+      col_o[i] = n_base + nt_o * 8 + (lane & 3) * 2;
+      valid[i] = has_out && row_o[i] < p.L_out && col_o[i] < p.Cout;
+      valid1[i] = valid[i] && col_o[i] + 1 < p.Cout;
+      v0[i] = 0.f;
+      v1[i] = 0.f;
+      if (has_out) {
+#pragma unroll
+        for (int w = 0; w < SM_WARPS; ++w) {
+          const float2 pr = *reinterpret_cast<const float2 *>(red + ((w * NQ + q) * 32 + lane) * 2);
+          v0[i] += pr.x;
+          v1[i] += pr.y;
+        }
+        v0[i] += p.bias[col_o[i]];
+        v1[i] += p.bias[col_o[i] + 1];
+      }
     }
   }
-  // ---- sum the warps' partial tiles: red[warp][q][lane][2], q = (mt, nt, row half)
-#pragma unroll
-  for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf)
-        *reinterpret_cast<float2 *>(red + ((warp * MT * 4 + (mt * 2 + nt) * 2 + hf) * 32 + lane) * 2) =
-            make_float2(acc[mt][nt][2 * hf], acc[mt][nt][2 * hf + 1]);
-  __syncthreads();
-  // thread -> one (row, column pair): q = tid / 32 enumerates (mt, nt, hf); MT = 1 leaves warps 4..7 without outputs
-  const int q = tid >> 5;
-  const bool has_out = q < MT * 4;
-  const int mt_o = q >> 2, nt_o = (q >> 1) & 1, hf_o = q & 1;
-  const int row = mt_o * 16 + (lane >> 2) + hf_o * 8;
-  const int col = n_base + nt_o * 8 + (lane & 3) * 2;
-  const bool valid = has_out && row < p.L_out && col < p.Cout;        // Cout is even whenever it is not the head
-  float v0 = 0.f, v1 = 0.f;
-  if (has_out) {
-#pragma unroll
-    for (int w = 0; w < SM_WARPS; ++w) {
-      const float2 pr = *reinterpret_cast<const float2 *>(red + ((w * MT * 4 + q) * 32 + lane) * 2);
-      v0 += pr.x;
-      v1 += pr.y;
-    }
-    v0 += p.bias[col];
-    v1 += p.bias[col + 1];
-  }
-  const bool valid1 = valid && col + 1 < p.Cout;
   if (p.gw > 0) {
     // ---- GroupNorm statistics over (L_out x gw): CTA partial, then the cluster's CTAs exchange theirs
-    float s1 = valid ? v0 + (valid1 ? v1 : 0.f) : 0.f;
-    float s2 = valid ? v0 * v0 + (valid1 ? v1 * v1 : 0.f) : 0.f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
-    if (lane == 0) { stat[2 + warp * 2] = s1; stat[3 + warp * 2] = s2; }
-    __syncthreads();
-    if (tid == 0) {
-      float a = 0.f, c2 = 0.f;
-      for (int w = 0; w < SM_WARPS; ++w) { a += stat[2 + w * 2]; c2 += stat[3 + w * 2]; }
-      stat[0] = a;
-      stat[1] = c2;
-    }
-    const int csize = p.gw / SM_NCH;
+    const int csize = p.gw / NCH;
     float t1 = 0.f, t2 = 0.f;
-    if (csize > 1) {
-      ptx::cluster_sync();
-      const uint32_t mine = ptx::smem_u32(stat);
-      for (int r = 0; r < csize; ++r) {
-        const float2 pr = ptx::ld_cluster_f32x2(ptx::mapa(mine, (uint32_t)r));
-        t1 += pr.x;
-        t2 += pr.y;
+    if (warp < SM_WARPS) {
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < QI; ++i) {
+        if (valid[i]) { s1 += v0[i]; s2 += v0[i] * v0[i]; }
+        if (valid1[i]) { s1 += v1[i]; s2 += v1[i] * v1[i]; }
       }
-      ptx::cluster_sync();          // nobody leaves while a peer may still read its statistics
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if (lane == 0) { stat[2 + warp * 2] = s1; stat[3 + warp * 2] = s2; }
+      ptx::named_bar_sync(1, SM_CONSUMERS);
+      if (tid == 0) {
+        float a = 0.f, c2 = 0.f;
+        for (int w = 0; w < SM_WARPS; ++w) { a += stat[2 + w * 2]; c2 += stat[3 + w * 2]; }
+        stat[0] = a;
+        stat[1] = c2;
+      }
+    }
+    if (csize > 1) {
+      ptx::cluster_sync();            // all 288 threads of every CTA of the cluster
+      const uint32_t mine = ptx::smem_u32(stat);
+      if (warp < SM_WARPS)
+        for (int r = 0; r < csize; ++r) {
+          const float2 pr = ptx::ld_cluster_f32x2(ptx::mapa(mine, (uint32_t)r));
+          t1 += pr.x;
+          t2 += pr.y;
+        }
+      ptx::cluster_sync();            // nobody leaves while a peer may still read its statistics
+      if (warp == SM_WARPS) return;
     } else {
-      __syncthreads();
+      ptx::named_bar_sync(1, SM_CONSUMERS);
       t1 = stat[0];
       t2 = stat[1];
     }
@@ -231,30 +295,36 @@ __global__ void __launch_bounds__(SM_THREADS, 1) conv_small_kernel(const ConvSma
     const float m = t1 * inv_n;
     const float var = fmaxf(t2 * inv_n - m * m, 0.f);
     const float rs = rsqrtf(var + kGnEps);
-    if (valid) {
-      v0 = mish_tc((v0 - m) * rs * p.gamma[col] + p.beta[col]);
-      v1 = mish_tc((v1 - m) * rs * p.gamma[col + 1] + p.beta[col + 1]);
-      if (p.ttab) {
-        v0 += p.ttab[(size_t)step * p.Cout + col];
-        v1 += p.ttab[(size_t)step * p.Cout + col + 1];
+#pragma unroll
+    for (int i = 0; i < QI; ++i)
+      if (valid[i]) {
+        const int col = col_o[i];
+        v0[i] = mish_tc((v0[i] - m) * rs * p.gamma[col] + p.beta[col]);
+        v1[i] = mish_tc((v1[i] - m) * rs * p.gamma[col + 1] + p.beta[col + 1]);
+        if (p.ttab) {
+          v0[i] += p.ttab[(size_t)step * p.Cout + col];
+          v1[i] += p.ttab[(size_t)step * p.Cout + col + 1];
+        }
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < QI; ++i)
+    if (valid[i]) {
+      const size_t o = ((size_t)b * p.L_out * p.out_mul + (size_t)row_o[i] * p.out_mul + p.out_phase) * p.Cout + col_o[i];
+      float a0 = v0[i], a1 = v1[i];
+      if (p.residual) {
+        const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162 *>(p.residual + o);
+        a0 += __low2float(r2);
+        a1 += __high2float(r2);
+      }
+      if (p.out_f32) {
+        float *op = reinterpret_cast<float *>(p.out) + o;
+        op[0] = a0;
+        if (valid1[i]) op[1] = a1;
+      } else {
+        *reinterpret_cast<__nv_bfloat162 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + o) = __floats2bfloat162_rn(a0, a1);
       }
     }
-  }
-  if (valid) {
-    const size_t o = ((size_t)b * p.L_out * p.out_mul + (size_t)row * p.out_mul + p.out_phase) * p.Cout + col;
-    if (p.residual) {
-      const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162 *>(p.residual + o);
-      v0 += __low2float(r2);
-      v1 += __high2float(r2);
-    }
-    if (p.out_f32) {
-      float *op = reinterpret_cast<float *>(p.out) + o;
-      op[0] = v0;
-      if (valid1) op[1] = v1;
-    } else {
-      *reinterpret_cast<__nv_bfloat162 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + o) = __floats2bfloat162_rn(v0, v1);
-    }
-  }
 }
 
 }  // namespace dad

@@ -22,6 +22,7 @@
 #include "step_kernel.cuh"
 
 #define STEP_FOR_EACH_SPT(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+#define SMALL_FOR_EACH(X) X(1, 2) X(2, 2) X(1, 4) X(2, 4)
 
 using namespace dad;
 
@@ -59,7 +60,7 @@ struct ConvOp {
   ConvT3Params t3p{};
   // small-batch latency path (conv_small.cuh)
   bool small = false;
-  int sm_mt = 1, sm_cluster = 1, sm_smem = 0;
+  int sm_mt = 1, sm_nt = 2, sm_cluster = 1, sm_smem = 0;
   ConvSmallParams smp{};
 };
 
@@ -101,7 +102,7 @@ struct dad_handle {
   float *d_sched[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   bool have_weights = false, have_sched = false;
   bool rows_t = false;               // the forward being enqueued has per-row timesteps
-  int small_max_b = 8;               // batches up to this size take the latency kernels (DAD_SMALL_MAX_B, 0 = never)
+  int small_max_b = 24;              // batches up to this size take the latency kernels (DAD_SMALL_MAX_B, 0 = never)
   // projector
   float *d_Nt = nullptr, *d_Nrow = nullptr, *d_q = nullptr, *d_alpha = nullptr;
   int projD = 0;
@@ -624,8 +625,9 @@ int set_kernel_attrs(dad_handle *h) {
 #define STEP_ATTR(spt) CK(h, cudaFuncSetAttribute(step_project_fused_kernel<spt>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   STEP_FOR_EACH_SPT(STEP_ATTR)
 #undef STEP_ATTR
-  CK(h, cudaFuncSetAttribute(conv_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-  CK(h, cudaFuncSetAttribute(conv_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+#define SMALL_ATTR(mt, nt) CK(h, cudaFuncSetAttribute(conv_small_kernel<mt, nt>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  SMALL_FOR_EACH(SMALL_ATTR)
+#undef SMALL_ATTR
   CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->step_ctas_per_sm, step_pointwise_kernel, 256, 0));
   if (h->step_ctas_per_sm < 1) h->step_ctas_per_sm = 1;
   return DAD_OK;
@@ -637,9 +639,11 @@ int set_kernel_attrs(dad_handle *h) {
 void setup_small_op(dad_handle *h, ConvOp &op) {
   const ConvGeom &g = op.g;
   op.small = false;
-  if (!h->bf16 || g.L_out > SM_MAX_L || op.Cout_pad % SM_NCH) return;
+  if (!h->bf16 || g.L_out > SM_MAX_L) return;
   const int gw = op.gname.empty() ? 0 : g.Cout / kGroups;
-  if (gw && (gw % SM_NCH || gw / SM_NCH > 8)) return;
+  // channels per CTA: 16, or 32 when a GroupNorm group would otherwise span more than 8 CTAs (the portable cluster limit)
+  const int nch = (gw && gw / 16 > 8) ? 32 : 16;
+  if (op.Cout_pad % nch || (gw && (gw % nch || gw / nch > 8))) return;
   int lo = 0, hi = 0;
   for (int t = 0; t < g.taps; ++t) { lo = std::min(lo, g.tap_off[t]); hi = std::max(hi, g.tap_off[t]); }
   ConvSmallParams &p = op.smp;
@@ -647,9 +651,21 @@ void setup_small_op(dad_handle *h, ConvOp &op) {
   p.halo = -lo;
   p.rows = p.halo + g.L_in + std::max(0, (g.L_out - 1) * g.in_stride + hi - (g.L_in - 1));
   op.sm_mt = g.L_out <= 16 ? 1 : 2;
-  op.sm_smem = (int)small_layout(g.C1 + g.C2, g.taps, p.rows, op.sm_mt).total;
+  op.sm_nt = nch / 8;
+  // weight ring: the whole K when it fits (every chunk then streams in ahead of the dependency wait), else 3 stages
+  const int Cin = g.C1 + g.C2, K = g.taps * Cin;
+  p.kc = K;
+  p.n_stages = 1;
+  if ((int)small_layout(Cin, p.rows, op.sm_mt, nch, p.kc, 1).total > h->max_smem_optin) {
+    p.n_stages = 3;
+    const int fixed = (int)small_layout(Cin, p.rows, op.sm_mt, nch, 0, 0).total;
+    const int per_row = (h->max_smem_optin - fixed) / (p.n_stages * nch) - 16;      // bytes of K per weight row and stage
+    p.kc = per_row / 2 / 128 * 128;             // whole k16 steps for each of the 8 warps
+    if (p.kc < 256) return;
+  }
+  op.sm_smem = (int)small_layout(Cin, p.rows, op.sm_mt, nch, p.kc, p.n_stages).total;
   if (op.sm_smem > h->max_smem_optin) return;
-  op.sm_cluster = gw ? gw / SM_NCH : 1;
+  op.sm_cluster = gw ? gw / nch : 1;
   p.in1 = reinterpret_cast<const __nv_bfloat16 *>(act_ptr(h, op.in1));
   p.in2 = op.in2 >= 0 ? reinterpret_cast<const __nv_bfloat16 *>(act_ptr(h, op.in2)) : nullptr;
   p.w = op.w_b16;
@@ -676,10 +692,11 @@ void setup_small_op(dad_handle *h, ConvOp &op) {
 }
 
 int enqueue_small(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
-  const dim3 grid((unsigned)(op.Cout_pad / SM_NCH), (unsigned)B);
-  const cudaError_t e = op.sm_mt == 1
-      ? launch_k(conv_small_kernel<1>, grid, dim3(SM_THREADS), (size_t)op.sm_smem, st, op.sm_cluster, op.smp)
-      : launch_k(conv_small_kernel<2>, grid, dim3(SM_THREADS), (size_t)op.sm_smem, st, op.sm_cluster, op.smp);
+  const dim3 grid((unsigned)(op.Cout_pad / (8 * op.sm_nt)), (unsigned)B);
+  cudaError_t e = cudaErrorInvalidValue;
+#define SMALL_CASE(mt, nt) if (op.sm_mt == mt && op.sm_nt == nt) e = launch_k(conv_small_kernel<mt, nt>, grid, dim3(SM_THREADS), (size_t)op.sm_smem, st, op.sm_cluster, op.smp);
+  SMALL_FOR_EACH(SMALL_CASE)
+#undef SMALL_CASE
   if (e != cudaSuccess) DAD_FAIL(h, DAD_ERR_CUDA, "conv_small launch failed for %s: %s", op.wname.c_str(), cudaGetErrorString(e));
   h->counting += 1;
   return DAD_OK;
@@ -691,7 +708,11 @@ static bool step_fused_fits(const dad_handle *h) {
 }
 
 int enqueue_tc(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
-  if (op.small && B <= h->small_max_b && !h->rows_t) return enqueue_small(h, op, B, st);
+  // latency kernels: every sample's CTAs fetch the layer's weights again, so past a re-read budget (256 MB per
+  // layer and launch: never reached by PointMaze below 24 samples, 6 samples of HalfCheetah's largest layer) the throughput kernels win
+  if (op.small && B <= h->small_max_b && !h->rows_t &&
+      (size_t)B * op.Cout_pad * op.g.taps * op.Cin_store * 2 <= ((size_t)256 << 20))
+    return enqueue_small(h, op, B, st);
   if (op.t3 && !h->rows_t) return enqueue_t3(h, op, B, st);      // conv_t3 assumes one timestep for the whole batch
   ConvTcParams p = op.tcp;
   p.B = B;

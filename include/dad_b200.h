@@ -168,7 +168,8 @@ int64_t dad_launch_count(const dad_handle *h);
 /* Batches of at most `max_b` samples run the latency kernels (one CTA per 16 output channels of a sample,
  * weights prefetched across the launch boundary): the shape of GuidedPolicy.get_action, which plans ONE
  * trajectory per call (policies.py:193-223).  Larger batches run the throughput kernels.  0 disables the
- * latency kernels; the default is 8 (or the DAD_SMALL_MAX_B environment variable).  bf16 mode only. */
+ * latency kernels; the default is 24, about where the throughput kernels take over on a B200 (or the
+ * DAD_SMALL_MAX_B environment variable).  bf16 mode only. */
 int dad_set_latency_batch(dad_handle *h, int32_t max_b);
 
 /* ---- measurement hooks (bench.py; no reference counterpart) ------------------------------------ */

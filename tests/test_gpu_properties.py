@@ -91,7 +91,10 @@ def test_large_batch_rows_equal_small_batch_rows(pointmaze_full):
 
 
 @pytest.mark.parametrize("arch", [dict(dim=128, mults=(1, 2, 4), H=32, T=6), dict(dim=64, mults=(1, 4, 8), H=32, T=23),
-                                  dict(dim=64, mults=(1, 2, 4, 8), H=16, T=67)])
+                                  dict(dim=64, mults=(1, 2, 4, 8), H=16, T=67),
+                                  # the real HalfCheetah widths: 256-wide GroupNorm groups (32-channel CTAs) and
+                                  # weight slabs that stream through the shared-memory ring
+                                  dict(dim=256, mults=(1, 4, 8), H=32, T=23)])
 def test_latency_kernels_match_throughput_kernels(arch):
     """get_action's single-plan shape: the small-batch kernels (conv_small) against the throughput kernels on the
     same weights and inputs -- same bf16 contract, different summation order -- and row independence within them."""
@@ -131,7 +134,8 @@ def test_chunking_equals_single_pass():
     sd, _ = helpers.make_state_dict(c)
     outs = []
     for cap in (64, 24):
-        net = TemporalUnet(6, dim=64, dim_mults=(1, 2), precision="bf16", max_batch=cap)
+        # latency_max_batch=0: both capacities run the same (throughput) kernels, so the comparison is bitwise
+        net = TemporalUnet(6, dim=64, dim_mults=(1, 2), precision="bf16", max_batch=cap, latency_max_batch=0)
         dif = GaussianDiffusion(net, horizon=16, observation_dim=4, action_dim=2, n_timesteps=20)
         dif.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
         dif.to(_dev())
