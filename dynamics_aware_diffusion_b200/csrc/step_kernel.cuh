@@ -112,10 +112,17 @@ struct StepView {
   float cr, crm1, c1, c2, sig, gvar;
 };
 
+// Values every thread loads from the same address: the shuffle tells the compiler they are warp-uniform, so the
+// Philox key schedule and the step coefficients live in uniform registers instead of being recomputed per thread.
+__device__ __forceinline__ unsigned uniform32(unsigned v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ unsigned long long uniform64(unsigned long long v) {
+  return ((unsigned long long)uniform32((unsigned)(v >> 32)) << 32) | uniform32((unsigned)v);
+}
+
 __device__ __forceinline__ StepView step_view(const StepParams &p) {
   const LoopState *ls = p.ls;
   StepView v;
-  const int i = ls->step;
+  const int i = (int)uniform32((unsigned)ls->step);
   v.step = i;
   v.x = ls->x;
   const float *nz = ls->noise;
@@ -123,8 +130,8 @@ __device__ __forceinline__ StepView step_view(const StepParams &p) {
   v.grad = ls->grad;
   float *tr = ls->trace;
   v.trace = tr ? tr + (size_t)(ls->n_steps - 1 - i) * ls->trace_stride : nullptr;
-  v.seed = ls->seed;
-  v.sample_offset = ls->sample_offset;
+  v.seed = uniform64(ls->seed);
+  v.sample_offset = uniform64(ls->sample_offset);
   v.flags = ls->flags;
   v.n_cond = (v.flags & 1u) ? ls->n_cond : 0;
   const int per_batch = ls->cond_per_batch;
@@ -161,6 +168,23 @@ __device__ __forceinline__ void step_math4(const StepParams &p, const StepView &
     zv[0] = z4.x; zv[1] = z4.y; zv[2] = z4.z; zv[3] = z4.w;
   }
   if (v.gvar != 0.f) { gv[0] = q.g.x; gv[1] = q.g.y; gv[2] = q.g.z; gv[3] = q.g.w; }
+  if (p.predict_epsilon && p.clip_denoised && v.gvar == 0.f) {
+    // the usual configuration (epsilon prediction, clipping, no guidance gradient) on packed fp32x2; the same
+    // operations in the same order as the general path below, so the results are bit-identical
+    const f32x2 cr2 = pk2(v.cr, v.cr), ncrm1 = pk2(-v.crm1, -v.crm1), c12 = pk2(v.c1, v.c1), c22 = pk2(v.c2, v.c2);
+    const f32x2 sg2 = pk2(v.sig, v.sig);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const f32x2 x2 = pk2(xv[2 * h], xv[2 * h + 1]);
+      float a, b2;
+      upk2(ffma2(cr2, x2, fmul2(ncrm1, pk2(mv[2 * h], mv[2 * h + 1]))), a, b2);
+      a = fminf(fmaxf(a, -1.f), 1.f);
+      b2 = fminf(fmaxf(b2, -1.f), 1.f);
+      const f32x2 mu = ffma2(c22, x2, fmul2(c12, pk2(a, b2)));
+      upk2(ffma2(sg2, pk2(zv[2 * h], zv[2 * h + 1]), mu), out[2 * h], out[2 * h + 1]);
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     float x0 = p.predict_epsilon ? (v.cr * xv[j] - v.crm1 * mv[j]) : mv[j];
