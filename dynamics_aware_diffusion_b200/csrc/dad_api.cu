@@ -102,6 +102,8 @@ struct dad_handle {
   float *d_sched[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   bool have_weights = false, have_sched = false;
   bool rows_t = false;               // the forward being enqueued has per-row timesteps
+  long long epoch = 0;               // bumped whenever captured pointers / kernel choices go stale
+  long long loop_kernels = 0;        // kernels of the last dad_loop_unet + dad_loop_step pair
   int small_max_b = 24;              // batches up to this size take the latency kernels (DAD_SMALL_MAX_B, 0 = never)
   // projector
   float *d_Nt = nullptr, *d_Nrow = nullptr, *d_q = nullptr, *d_alpha = nullptr;
@@ -928,6 +930,7 @@ void fill_cond(const dad_handle *h, LoopState &ls, int row0) {
 }
 
 void drop_graphs(dad_handle *h) {
+  h->epoch += 1;            // caller-captured steps (dad_loop_*) point at the same buffers
   for (auto &kv : h->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   h->graphs.clear();
@@ -1458,6 +1461,81 @@ int dad_sample(dad_handle *h, float *x, const float *noise_seq, uint64_t seed, u
     for (int s = 0; s < n_steps; ++s) CK(h, cudaGraphLaunch(ge->exec, st));
     h->launches += ge->kernels * n_steps;
   }
+  return DAD_OK;
+}
+
+static bool stream_is_capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
+}
+
+int dad_loop_begin(dad_handle *h, float *x, const float *noise, int32_t noise_single, const float *grad, float guide_w,
+                   uint64_t seed, uint64_t sample_offset, int32_t B, int32_t n_steps, uint32_t flags, float *trace,
+                   void *stream) {
+  if (!h || !x || B < 1) return DAD_ERR_INVALID;
+  if (!h->have_weights || !h->have_sched) DAD_FAIL(h, DAD_ERR_STATE, "dad_loop_begin before weights and schedule are set");
+  if (B > h->cfg.max_batch) DAD_FAIL(h, DAD_ERR_INVALID, "dad_loop_begin needs B <= max_batch (%d)", h->cfg.max_batch);
+  if (n_steps < 1 || n_steps > h->cfg.n_timesteps)
+    DAD_FAIL(h, DAD_ERR_INVALID, "n_steps %d outside [1, %d] (the schedule tables have n_timesteps entries)", n_steps, h->cfg.n_timesteps);
+  if ((flags & DAD_FLAG_PROJECT) && !h->projD) DAD_FAIL(h, DAD_ERR_STATE, "DAD_FLAG_PROJECT without dad_set_projector");
+  if ((flags & DAD_FLAG_CONDITIONS) && h->n_cond && h->cond_per_batch && h->cond_B != B)
+    DAD_FAIL(h, DAD_ERR_INVALID, "per-batch conditions were registered for B=%d, sampling B=%d", h->cond_B, B);
+  CK(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  LoopState ls{};
+  ls.step = n_steps;            // dad_loop_unet decrements it first
+  ls.n_steps = n_steps;
+  ls.flags = flags;
+  ls.guide_w = guide_w;
+  ls.x = x;
+  ls.noise = noise;
+  ls.noise_stride = noise_single ? 0 : (long long)B * h->D;
+  ls.grad = grad;
+  ls.trace = trace;
+  ls.trace_stride = (long long)B * h->D;
+  ls.seed = seed;
+  ls.sample_offset = sample_offset;
+  fill_cond(h, ls, 0);
+  int rc = set_loop_state(h, ls, st);
+  if (rc) return rc;
+  const bool draw = (flags & DAD_FLAG_PHILOX_INIT) != 0;
+  if (draw || ((flags & DAD_FLAG_CONDITIONS) && h->n_cond)) {
+    init_x_kernel<<<cdiv((size_t)B * h->D / 4, 256), 256, 0, st>>>(h->d_ls, h->d_cond, B, h->D, h->cfg.transition_dim, draw ? 1 : 0);
+    h->launches += 1;
+    CK(h, cudaGetLastError());
+  }
+  return DAD_OK;
+}
+
+int dad_loop_unet(dad_handle *h, int32_t B, void *stream) {
+  if (!h || B < 1 || B > h->cfg.max_batch) return DAD_ERR_INVALID;
+  if (!h->have_weights) DAD_FAIL(h, DAD_ERR_STATE, "dad_loop_unet before dad_load_weights");
+  CK(h, cudaSetDevice(h->cfg.device));
+  h->counting = 0;
+  const int rc = enqueue_unet(h, B, reinterpret_cast<cudaStream_t>(stream), true, nullptr);
+  h->loop_kernels = h->counting;
+  if (!stream_is_capturing(reinterpret_cast<cudaStream_t>(stream))) h->launches += h->counting;
+  return rc;
+}
+
+int dad_loop_step(dad_handle *h, int32_t B, uint32_t flags, void *stream) {
+  if (!h || B < 1 || B > h->cfg.max_batch) return DAD_ERR_INVALID;
+  if (!h->have_sched) DAD_FAIL(h, DAD_ERR_STATE, "dad_loop_step before dad_set_schedule");
+  const bool project = (flags & DAD_FLAG_PROJECT) != 0;
+  if (project && !h->projD) DAD_FAIL(h, DAD_ERR_STATE, "DAD_FLAG_PROJECT without dad_set_projector");
+  CK(h, cudaSetDevice(h->cfg.device));
+  h->counting = 0;
+  const int rc = enqueue_step(h, h->d_eps, B, project, false, reinterpret_cast<cudaStream_t>(stream));
+  h->loop_kernels += h->counting;
+  if (!stream_is_capturing(reinterpret_cast<cudaStream_t>(stream))) h->launches += h->counting;
+  return rc;
+}
+
+int64_t dad_graph_epoch(const dad_handle *h) { return h ? h->epoch : -1; }
+
+int dad_loop_replayed(dad_handle *h, int32_t n) {
+  if (!h || n < 0) return DAD_ERR_INVALID;
+  h->launches += h->loop_kernels * n;
   return DAD_OK;
 }
 

@@ -148,6 +148,32 @@ class Engine:
         self._keep = [x, model_out, noise, grad]
         return x
 
+    # ---- guided sampling inside a caller-captured CUDA graph (dad_loop_*) -----------------------------
+    def loop_begin(self, x, n_steps, noise=None, noise_single=False, grad=None, guide_w=0.0, flags=0, seed=0,
+                   sample_offset=0, trace=None):
+        """Put the loop state on the device: x in/out, noise None (Philox) | (n_steps,B,H,T) | one reused (B,H,T)
+        slot, grad = the buffer the caller's guidance writes every step."""
+        x = _f32c(x, "x")
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.dad_loop_begin(self.handle, _ptr(x), _ptr(noise), 1 if noise_single else 0, _ptr(grad),
+                                             float(guide_w), int(seed), int(sample_offset), x.shape[0], int(n_steps),
+                                             int(flags), _ptr(trace), _stream()))
+        self._keep = [x, noise, grad, trace]
+
+    def loop_unet(self, B):
+        """Enqueue `step -= 1; eps = unet(x)` on the current stream (capturable)."""
+        self._ck(self.lib.dad_loop_unet(self.handle, int(B), _stream()))
+
+    def loop_step(self, B, flags=0):
+        """Enqueue the fused remainder of the step (reads eps, grad, noise; writes x) on the current stream (capturable)."""
+        self._ck(self.lib.dad_loop_step(self.handle, int(B), int(flags), _stream()))
+
+    def graph_epoch(self):
+        return int(self.lib.dad_graph_epoch(self.handle))
+
+    def loop_replayed(self, n):
+        self._ck(self.lib.dad_loop_replayed(self.handle, int(n)))
+
     def project(self, x, step):
         x = _f32c(x, "x")
         with torch.cuda.device(self.device):

@@ -16,6 +16,9 @@ x_{i-1} = project(denoise(x_i))).  In the reference `apply_projection` exists bu
 """
 from typing import Callable, Dict, Optional
 
+import os
+import warnings
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -23,6 +26,10 @@ import torch.nn as nn
 from . import _native as N
 from .diffusion import _run_loop
 from .projection import fold_projection, projection_alphas
+
+
+class _CaptureFailed(RuntimeError):
+    """The guidance function could not be captured into a CUDA graph."""
 
 
 class GuidedPolicy(nn.Module):
@@ -39,6 +46,11 @@ class GuidedPolicy(nn.Module):
         self.transition_dim = diffusion_model.transition_dim
         self.action_horizon = action_horizon if action_horizon is not None else 1
         self.action_buffer = []
+        # guided loops: capture one step (our kernels + the guide's autograd) in a CUDA graph and replay it; falls
+        # back to a per-step host loop, for good, the first time the guide_fn turns out not to be capturable
+        self.capture_guidance = os.environ.get("DAD_GUIDED_GRAPH", "1") != "0"
+        self._guided_graphs = {}
+        self._capture_error = None
 
     # ---- hooks overridden by DynamicsAwarePolicy --------------------------------------------------
     def _loop_flags(self, engine):
@@ -103,6 +115,13 @@ class GuidedPolicy(nn.Module):
         x = x.contiguous()
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        if self.capture_guidance and batch_size <= self.diffusion.model.max_batch:
+            try:
+                return self._guided_loop_graph(eng, x, noise, rng, seed, flags, return_trace, sample_offset)
+            except _CaptureFailed as exc:
+                # a guide_fn that cannot run under stream capture (host syncs, CPU work): per-step host loop
+                self.capture_guidance = False
+                self._capture_error = str(exc)
         trace = []
         for k, i in enumerate(reversed(range(S))):
             t = torch.full((batch_size,), i, device=device, dtype=torch.long)
@@ -119,6 +138,78 @@ class GuidedPolicy(nn.Module):
             if return_trace:
                 trace.append(x.clone())
         return (x, torch.stack(trace)) if return_trace else x
+
+    def _guided_loop_graph(self, eng, x_init, noise, rng, seed, flags, return_trace, sample_offset):
+        """The guided loop with ONE captured step replayed S times: our kernels and the value
+        model's forward+backward (policies.py:87-97, gradient at x_t) live in the same CUDA graph, the step index
+        on the device.  The captured step is cached per (batch, flags, noise mode) and re-captured when the
+        native handle reallocates what it points to."""
+        S = self.diffusion.n_timesteps
+        B = x_init.shape[0]
+        device = x_init.device
+        mode = "seq" if noise is not None else ("torch" if rng == "torch" else "philox")
+        key = (B, int(flags), mode, device.index or 0)
+        ent = self._guided_graphs.get(key)
+        if ent is None or ent["epoch"] != eng.graph_epoch() or ent["engine"] is not eng:
+            ent = dict(engine=eng, x=torch.empty_like(x_init), grad=torch.zeros_like(x_init),
+                       t=torch.zeros(B, device=device, dtype=torch.long),
+                       z=torch.empty_like(x_init) if mode == "torch" else None)
+            ent["x"].copy_(x_init)
+            ent["t"].fill_(S)
+            # warm-up on a side stream (lazy initialisation inside the user's model must not happen under capture)
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                self._guidance_grad(ent["x"], ent["t"] - 1)
+                # second, checked run: a guide that synchronises with the host (.item(), .cpu(), CPU tensors) cannot
+                # be captured, and a capture that fails half-way leaves torch's CUDA generator unusable -- so find
+                # out here, in eager mode, where the only consequence is an exception
+                prev = torch.cuda.get_sync_debug_mode()
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")          # "prototype feature" notice
+                    torch.cuda.set_sync_debug_mode("error")
+                try:
+                    self._guidance_grad(ent["x"], ent["t"] - 1)
+                except RuntimeError as exc:
+                    raise _CaptureFailed("guide_fn synchronises with the host: %s" % str(exc).splitlines()[0]) from exc
+                finally:
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore")
+                        torch.cuda.set_sync_debug_mode(prev)
+            torch.cuda.current_stream(device).wait_stream(side)
+            torch.cuda.synchronize(device)
+            graph = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(graph):
+                    ent["t"].sub_(1)
+                    eng.loop_unet(B)
+                    ent["grad"].copy_(self._guidance_grad(ent["x"], ent["t"]))
+                    if ent["z"] is not None:
+                        ent["z"].normal_()
+                    eng.loop_step(B, flags)
+            except Exception as exc:          # torch reports capture violations as RuntimeError
+                raise RuntimeError("capturing the guided step into a CUDA graph failed (%s); torch's CUDA RNG state may "
+                                   "be unusable in this process now.  Set policy.capture_guidance = False (or "
+                                   "DAD_GUIDED_GRAPH=0) for this guide_fn." % str(exc).splitlines()[0]) from exc
+            ent["graph"] = graph
+            ent["epoch"] = eng.graph_epoch()
+            self._guided_graphs = {key: ent}       # one captured step alive at a time
+        ent["x"].copy_(x_init)
+        ent["t"].fill_(S)
+        trace = torch.empty((S,) + tuple(x_init.shape), device=device) if return_trace else None
+        if mode == "seq":
+            zseq = noise.to(device, torch.float32).contiguous()
+            if zseq.shape[0] < S or tuple(zseq.shape[1:]) != tuple(x_init.shape):
+                raise ValueError("noise must be (n_timesteps, B, H, T)")
+        else:
+            zseq = ent["z"]
+        eng.loop_begin(ent["x"], S, noise=zseq, noise_single=(mode == "torch"), grad=ent["grad"],
+                       guide_w=float(self.guide_weight), flags=flags, seed=seed, sample_offset=sample_offset, trace=trace)
+        for _ in range(S):
+            ent["graph"].replay()
+        eng.loop_replayed(S)
+        out = ent["x"].clone()
+        return (out, trace) if return_trace else out
 
     # ---- environment-facing glue (host side) ----------------------------------------------------------
     def _process_observation(self, observation):

@@ -172,6 +172,28 @@ int64_t dad_launch_count(const dad_handle *h);
  * DAD_SMALL_MAX_B environment variable).  bf16 mode only. */
 int dad_set_latency_batch(dad_handle *h, int32_t max_b);
 
+/* ---- guided sampling inside a caller-captured CUDA graph -------------------------------------------
+ * ValueGuidedPolicy (policies.py:243-271) differentiates a user value model at x_t every step
+ * (policies.py:87-97).  That forward+backward is the caller's (PyTorch's) work; to keep it out of a per-step
+ * host loop the caller captures ONE step into its own CUDA graph --
+ *     dad_loop_unet;  <its guidance kernels writing `grad`>;  dad_loop_step
+ * -- and replays it n_steps times.  dad_loop_begin puts the loop state on the device first (not captured):
+ * x (B,H,T) in/out; noise: NULL = in-kernel Philox, else n_steps slots of (B,H,T) consumed in order, or ONE slot
+ * the caller refills every step when noise_single != 0; grad: the (B,H,T) buffer the guidance writes (NULL = no
+ * guidance); trace: NULL or (n_steps,B,H,T).  B <= max_batch.  The step index lives on the device and is
+ * decremented by dad_loop_unet, so the captured step is the same for every index.  dad_loop_unet and
+ * dad_loop_step only enqueue kernels (legal under stream capture); flags as dad_step.
+ * dad_graph_epoch changes whenever buffers a captured step points to were reallocated (conditions grown,
+ * projector replaced, weights reloaded, latency batch changed): re-capture when it differs.
+ * dad_loop_replayed adds n replays of the last captured step to dad_launch_count. */
+int dad_loop_begin(dad_handle *h, float *x, const float *noise, int32_t noise_single, const float *grad, float guide_w,
+                   uint64_t seed, uint64_t sample_offset, int32_t B, int32_t n_steps, uint32_t flags, float *trace,
+                   void *stream);
+int dad_loop_unet(dad_handle *h, int32_t B, void *stream);
+int dad_loop_step(dad_handle *h, int32_t B, uint32_t flags, void *stream);
+int64_t dad_graph_epoch(const dad_handle *h);
+int dad_loop_replayed(dad_handle *h, int32_t n);
+
 /* ---- measurement hooks (bench.py; no reference counterpart) ------------------------------------ */
 
 /* dad_sample with Philox noise that also returns the device time of every diffusion step (CUDA events

@@ -192,6 +192,53 @@ def test_conditioned_and_value_guided_steps(name, precision, monkeypatch):
     assert worst_excess(errs, tols) < 1.0, errs
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16-latency"])
+@pytest.mark.parametrize("name", ["tiny", "pointmaze", "cheetah_s"])
+def test_value_guided_loop_graph_equals_host_loop(name, precision, monkeypatch):
+    """ValueGuidedPolicy.sample_loop: the captured step (our kernels + the value model's autograd in one CUDA
+    graph, step index on the device) against the per-step host loop and against the reference's free-running
+    value-guided trace; a guide_fn that cannot be captured falls back to the host loop."""
+    from dynamics_aware_diffusion_b200 import ValueGuidedPolicy
+    c, g, dif, sd = models(name, precision)
+
+    class ValueModel(torch.nn.Module):
+        def __init__(self, w):
+            super().__init__()
+            self.w = torch.nn.Parameter(w)
+
+        def forward(self, obs):
+            return torch.tanh(obs @ self.w)
+
+    vm = ValueModel(cu(helpers.value_weights(c)))
+    cond0 = {0: cu(g["start"])[None]}
+    x_init = cu(g["x_init"])
+    monkeypatch.setattr(torch, "randn", lambda *a, **k: x_init.clone())
+    outs = {}
+    for mode in ("graph", "host"):
+        vpol = ValueGuidedPolicy(dif, helpers.normalizer(c), vm, guide_weight=float(g["value_guide_weight"]))
+        vpol.capture_guidance = mode == "graph"
+        x, trace = vpol.sample_loop(batch_size=c["B"], conditions=cond0, noise=cu(g["noise"]), return_trace=True)
+        if mode == "graph":
+            assert vpol.capture_guidance, "capture failed: %s" % vpol._capture_error
+            # the cached captured step serves the next call (other conditions, Philox noise)
+            x2 = vpol.sample_loop(batch_size=c["B"], conditions={0: cu(g["goal"])[None]}, seed=3)
+            assert bool(torch.isfinite(x2).all()) and bool((x2[:, 0] == cu(g["goal"])).all())
+            x3 = vpol.sample_loop(batch_size=c["B"], conditions=cond0, noise=cu(g["noise"]))
+            assert torch.equal(x3, x)
+        outs[mode] = (x, trace)
+        assert torch.equal(trace[-1], x)
+    assert helpers.rel_l2(outs["graph"][1].cpu().numpy(), outs["host"][1].cpu().numpy()) < 1e-6
+    assert helpers.rel_l2(outs["graph"][1].cpu().numpy(), g["trace_value"]) < FREE_TOL[precision]
+
+    # not capturable: the guide synchronises with the host
+    vpol = ValueGuidedPolicy(dif, helpers.normalizer(c), vm, guide_weight=float(g["value_guide_weight"]))
+    inner = vpol.guide_fn
+    vpol.guide_fn = lambda x, t: inner(x, t) * float(t[0].item() >= 0)
+    x = vpol.sample_loop(batch_size=c["B"], conditions=cond0, noise=cu(g["noise"]))
+    assert not vpol.capture_guidance and vpol._capture_error
+    assert helpers.rel_l2(x.cpu().numpy(), outs["host"][0].cpu().numpy()) < 1e-6
+
+
 @pytest.mark.parametrize("name", CASE_NAMES)
 def test_apply_projection(name):
     """DynamicsAwarePolicy.apply_projection (one affine map on the device) vs the reference's 15-op chain."""
