@@ -20,6 +20,7 @@
 #include "conv_small.cuh"
 #include "kernels_f32.cuh"
 #include "step_kernel.cuh"
+#include "projector_build.cuh"
 
 #define STEP_FOR_EACH_SPT(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
 #define SMALL_FOR_EACH(X) X(1, 2) X(2, 2) X(1, 4) X(2, 4)
@@ -1532,6 +1533,25 @@ int dad_loop_step(dad_handle *h, int32_t B, uint32_t flags, void *stream) {
 }
 
 int64_t dad_graph_epoch(const dad_handle *h) { return h ? h->epoch : -1; }
+
+int dad_build_projection_matrix(int32_t device, const double *F, int32_t rows, int32_t cols, float *P) {
+  char buf[256];
+  if (!F || !P || rows < 1 || cols < 1 || cols > rows) { g_create_error = "dad_build_projection_matrix: bad arguments"; return DAD_ERR_INVALID; }
+  cudaError_t e = cudaSetDevice(device);
+  int bad = 0;
+  if (e == cudaSuccess) e = build_projection_matrix(F, rows, cols, P, &bad);
+  if (e != cudaSuccess) {
+    snprintf(buf, sizeof(buf), "dad_build_projection_matrix: %s", cudaGetErrorString(e));
+    g_create_error = buf;
+    return DAD_ERR_CUDA;
+  }
+  if (bad) {
+    snprintf(buf, sizeof(buf), "dad_build_projection_matrix: F is not of full column rank (pivot %d of F^T F is not positive)", bad);
+    g_create_error = buf;
+    return DAD_ERR_INVALID;
+  }
+  return DAD_OK;
+}
 
 int dad_loop_replayed(dad_handle *h, int32_t n) {
   if (!h || n < 0) return DAD_ERR_INVALID;

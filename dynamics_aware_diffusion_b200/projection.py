@@ -37,8 +37,21 @@ class ProjectionMatrixBuilder:
         F[(T + 1) * n:, n:] = np.eye(T * m)
         return F
 
-    def get_projection_matrix(self, horizon: int) -> torch.Tensor:
+    def get_projection_matrix(self, horizon: int, device=None) -> torch.Tensor:
+        """P = F pinv(F) as an fp32 CPU tensor (projection.py:85-120).  `device` (extra, optional): a CUDA device --
+        the projector is then built there in fp64 (Gram matrix + Cholesky, `dad_build_projection_matrix`) instead of
+        numpy's SVD: the same P to fp32 rounding in milliseconds, for dynamics or horizons that change online."""
         F = self._build_F_matrix(horizon)
+        if device is not None:
+            from . import _native as N
+            dev = torch.device(device)
+            if dev.type != "cuda":
+                raise ValueError("device must be a CUDA device (the default, None, is the reference's numpy path)")
+            F = np.ascontiguousarray(F, dtype=np.float64)
+            P32 = np.empty((F.shape[0], F.shape[0]), dtype=np.float32)
+            rc = N.lib().dad_build_projection_matrix(dev.index or 0, F.ctypes.data, F.shape[0], F.shape[1], P32.ctypes.data)
+            N.check(None, rc)
+            return torch.from_numpy(P32)
         P = F @ np.linalg.pinv(F)
         if self.verbose:
             print("projection: F %s, ||P^2-P||_F = %.2e" % (F.shape, np.linalg.norm(P @ P - P)))

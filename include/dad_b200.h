@@ -194,6 +194,14 @@ int dad_loop_step(dad_handle *h, int32_t B, uint32_t flags, void *stream);
 int64_t dad_graph_epoch(const dad_handle *h);
 int dad_loop_replayed(dad_handle *h, int32_t n);
 
+/* ---- projector build on the device ---------------------------------------------------------------------
+ * P = F pinv(F), the orthogonal projector onto range(F) (ProjectionMatrixBuilder.get_projection_matrix,
+ * dynamics/projection.py:85-120: numpy SVD pinv in fp64, cast to fp32).  F: rows x cols fp64 row-major, HOST
+ * memory; P: rows x rows fp32, HOST memory.  fp64 Gram matrix + blocked Cholesky + triangular solve on `device`;
+ * F must have full column rank (the reference's F always has: its rows contain the identity), otherwise
+ * DAD_ERR_INVALID and dad_last_error(NULL) names the failing pivot.  No handle needed. */
+int dad_build_projection_matrix(int32_t device, const double *F, int32_t rows, int32_t cols, float *P);
+
 /* ---- measurement hooks (bench.py; no reference counterpart) ------------------------------------ */
 
 /* dad_sample with Philox noise that also returns the device time of every diffusion step (CUDA events

@@ -191,3 +191,44 @@ def test_errors_are_loud():
     strict = TemporalUnet(6, dim=64, dim_mults=(1, 2), precision="bf16")
     with pytest.raises(N.DadError):      # 12 rows per sample do not tile the 128-row MMA: bf16 refuses, loudly
         strict(torch.zeros(2, 12, 6, device=_dev()), torch.zeros(2, dtype=torch.long, device=_dev()))
+
+
+@pytest.mark.parametrize("name", ["pointmaze", "cheetah_s", "door_s"])
+def test_device_projector_build_matches_numpy_pinv(name):
+    """ProjectionMatrixBuilder.get_projection_matrix(H, device=cuda): fp64 Gram + Cholesky on the device against the
+    reference's numpy SVD pinv (projection.py:104-107), at fp32 rounding; P is symmetric and idempotent."""
+    from dynamics_aware_diffusion_b200 import ProjectionMatrixBuilder, fit_linear_dynamics
+    c = helpers.CASES[name]
+    dyn = helpers.dynamics(c)
+    A, B = dyn if len(dyn) == 2 else fit_linear_dynamics(dyn[2], dyn[3], dyn[4])
+    b = ProjectionMatrixBuilder(A, B, c["n"], c["m"])
+    want = b.get_projection_matrix(c["H"]).numpy()
+    got = b.get_projection_matrix(c["H"], device=_dev()).numpy()
+    assert got.shape == want.shape and got.dtype == np.float32
+    assert np.abs(got - want).max() < 2e-6, np.abs(got - want).max()
+    g64 = got.astype(np.float64)
+    assert np.abs(g64 @ g64 - g64).max() < 1e-5 and np.abs(g64 - g64.T).max() < 1e-6
+
+
+def test_device_projector_build_full_door_size_and_rank_check():
+    """D = 2183, rank 935 (AdroitHand Door, H = 32): the size SURVEY.md 8(f-4) names; and a rank-deficient F is refused."""
+    import time
+    from dynamics_aware_diffusion_b200 import ProjectionMatrixBuilder, synthetic, _native as N
+    A, B, *_ = synthetic.random_linear_system(39, 28, seed=11, n_transitions=1000)
+    b = ProjectionMatrixBuilder(A, B, 39, 28)
+    b.get_projection_matrix(4, device=_dev())          # context / module load
+    t0 = time.perf_counter()
+    got = b.get_projection_matrix(32, device=_dev()).numpy()
+    t_dev = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    want = b.get_projection_matrix(32).numpy()
+    t_np = time.perf_counter() - t0
+    print("Door projector (2183 x 2183): device %.1f ms, numpy %.1f ms" % (t_dev * 1e3, t_np * 1e3))
+    assert got.shape == (2183, 2183)
+    assert np.abs(got - want).max() < 5e-6, np.abs(got - want).max()
+    F = np.ones((8, 3))
+    F[:, 1] = np.arange(8)
+    F[:, 2] = F[:, 1] * 2 + 1          # a linear combination of the first two columns
+    P = np.empty((8, 8), dtype=np.float32)
+    rc = N.lib().dad_build_projection_matrix(0, F.ctypes.data, 8, 3, P.ctypes.data)
+    assert rc != 0 and b"full column rank" in N.lib().dad_last_error(None)
