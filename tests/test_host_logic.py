@@ -205,3 +205,23 @@ def test_dynamics_residual_matches_reference(name):
         got = dynamics_residual(g["trace_dyn"][k], P, nz.obs_mean, nz.obs_std, nz.action_mean, nz.action_std, c["n"], c["m"])
         want = float(g["residual_dyn"][k])
         assert abs(got - want) <= 1e-4 * max(want, 1e-3)
+
+
+def test_optional_knobs_do_not_change_the_reference_surface():
+    """The extras of this round (latency kernels, captured guidance, device projector build) are optional and
+    host-visible without a GPU: defaults keep the reference's behaviour, misuse raises."""
+    net = TemporalUnet(6, dim=64, dim_mults=(1, 2), latency_max_batch=0)
+    assert net.latency_max_batch == 0 and TemporalUnet(6, dim=64, dim_mults=(1, 2)).latency_max_batch is None
+    dif = GaussianDiffusion(net, horizon=16, observation_dim=4, action_dim=2, n_timesteps=20)
+    pol = GuidedPolicy(dif, helpers.normalizer(helpers.CASES["tiny"]), guide_fn=lambda x, t: x.sum((1, 2)))
+    assert pol.capture_guidance and pol._guided_graphs == {}
+    A, B = helpers.dynamics(helpers.CASES["tiny"])
+    b = ProjectionMatrixBuilder(A, B, 4, 2)
+    P = b.get_projection_matrix(16)                         # default: the reference's numpy path, CPU fp32 tensor
+    assert P.dtype == torch.float32 and P.device.type == "cpu" and b.verify_projection(P)
+    with pytest.raises(ValueError):
+        b.get_projection_matrix(16, device="cpu")
+    if not torch.cuda.is_available():
+        # the device build needs a GPU and says so through the C-ABI error channel
+        with pytest.raises(_native.DadError):
+            b.get_projection_matrix(16, device="cuda:0")
