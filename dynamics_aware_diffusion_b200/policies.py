@@ -148,7 +148,7 @@ class GuidedPolicy(nn.Module):
         B = x_init.shape[0]
         device = x_init.device
         mode = "seq" if noise is not None else ("torch" if rng == "torch" else "philox")
-        key = (B, int(flags), mode, device.index or 0)
+        key = (B, int(flags), mode, device.index or 0, id(self.guide_fn))      # the captured step calls THIS guide_fn
         ent = self._guided_graphs.get(key)
         if ent is None or ent["epoch"] != eng.graph_epoch() or ent["engine"] is not eng:
             ent = dict(engine=eng, x=torch.empty_like(x_init), grad=torch.zeros_like(x_init),
