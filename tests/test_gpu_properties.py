@@ -232,3 +232,45 @@ def test_device_projector_build_full_door_size_and_rank_check():
     P = np.empty((8, 8), dtype=np.float32)
     rc = N.lib().dad_build_projection_matrix(0, F.ctypes.data, 8, 3, P.ctypes.data)
     assert rc != 0 and b"full column rank" in N.lib().dad_last_error(None)
+
+
+@pytest.mark.parametrize("kind", ["mpc", "dynamics-aware", "value-guided"])
+def test_get_action_end_to_end(kind):
+    """GuidedPolicy.get_action (policies.py:193-223): observation -> normalise -> condition {0: [obs, 0]} -> ONE plan
+    (the latency kernels' shape) -> buffered, unnormalised actions; replans only when the buffer is empty."""
+    from dynamics_aware_diffusion_b200 import (TemporalUnet, GaussianDiffusion, MPCPolicy, DynamicsAwarePolicy,
+                                               ValueGuidedPolicy, ProjectionMatrixBuilder, synthetic)
+    net = TemporalUnet(6, dim=128, dim_mults=(1, 2, 4), precision="bf16", max_batch=8)
+    dif = GaussianDiffusion(net, horizon=32, observation_dim=4, action_dim=2, n_timesteps=12)
+    synthetic.fill_state_dict(dif, 0)
+    dif.to(_dev())
+    nz = synthetic.SyntheticNormalizer(4, 2)
+    if kind == "mpc":
+        pol = MPCPolicy(dif, nz, action_horizon=3)
+    elif kind == "dynamics-aware":
+        A, B = synthetic.double_integrator(0.1)
+        P = ProjectionMatrixBuilder(A, B, 4, 2).get_projection_matrix(32, device=_dev())
+        pol = DynamicsAwarePolicy(dif, projection_matrix=P, normalizer=nz, state_dim=4, observation_dim=4, action_dim=2,
+                                  horizon=32, projection_schedule="noise_schedule", action_horizon=3)
+    else:
+        value = torch.nn.Sequential(torch.nn.Linear(4, 16), torch.nn.Mish(), torch.nn.Linear(16, 1)).to(_dev())
+        pol = ValueGuidedPolicy(dif, nz, value, guide_weight=0.2, action_horizon=3)
+    obs = np.array([0.4, -0.1, 0.2, 0.05])
+    torch.manual_seed(21)
+    a0 = pol.get_action({"observation": obs, "desired_goal": np.zeros(2), "achieved_goal": obs[:2]})
+    assert a0.shape == (2,) and np.isfinite(a0).all()
+    assert len(pol.action_buffer) == 3                       # range(0, action_horizon + 1) filled, one popped
+    # the same plan, made by hand
+    torch.manual_seed(21)
+    start = torch.zeros(1, 6, device=_dev())
+    start[:, :4] = torch.as_tensor(nz.normalize_observations(obs[None]), dtype=torch.float32)
+    plan = pol.sample_loop(batch_size=1, conditions={0: start})
+    assert bool((plan[:, 0] == start).all())
+    want = nz.unnormalize_actions(plan[0, :4, 4:].cpu().numpy())
+    np.testing.assert_allclose(a0, want[0], rtol=1e-6, atol=1e-7)
+    launches = pol._engine(_dev()).launch_count()
+    for k in range(1, 4):                                     # buffered actions: no device work
+        np.testing.assert_allclose(pol.get_action(obs), want[k], rtol=1e-6, atol=1e-7)
+    assert pol._engine(_dev()).launch_count() == launches
+    pol.get_action(obs)                                       # buffer empty -> replans
+    assert pol._engine(_dev()).launch_count() > launches and len(pol.action_buffer) == 3
