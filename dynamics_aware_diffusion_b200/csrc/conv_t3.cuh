@@ -26,18 +26,30 @@ namespace dad {
 
 constexpr int T3_BN = 128;
 constexpr int T3_BK = 64;
-#ifndef DAD_T3_CW
-#define DAD_T3_CW 16
-#endif
 #ifndef DAD_T3_NB
 #define DAD_T3_NB 6
 #endif
 constexpr int T3_NB = DAD_T3_NB;    // weight-tile ring (<= 8)
-#ifndef DAD_T3_NWG
-#define DAD_T3_NWG 3
+// Epilogue shape per GroupNorm width, measured per layer: the C=512 layers (GW 64; also GW 128) are
+// MMA-bound and run best with 3 epilogue warpgroups reading 16 TMEM columns at a time; everything else is bound
+// by the epilogue's critical path -- an item of an L=32 layer has 4 units of work -- and gains 1-3 us per layer
+// from a 4th warpgroup, which fits the register file only with 8-column chunks.  -DDAD_T3_NWG / -DDAD_T3_CW force
+// one shape for every instantiation (experiments).
+__host__ __device__ constexpr int t3_nwg(int gw) {
+#ifdef DAD_T3_NWG
+  return DAD_T3_NWG;
+#else
+  return (gw == 64 || gw == 128) ? 3 : 4;
 #endif
-constexpr int T3_NWG = DAD_T3_NWG;  // epilogue warpgroups; each takes every T3_NWG-th 128-column unit
-constexpr int T3_THREADS = 64 + 128 * T3_NWG;     // producer, MMA issuer, epilogue warpgroups
+}
+__host__ __device__ constexpr int t3_cw(int gw) {
+#ifdef DAD_T3_CW
+  return DAD_T3_CW;
+#else
+  return (gw == 64 || gw == 128) ? 16 : 8;
+#endif
+}
+__host__ __device__ constexpr int t3_threads(int gw) { return 64 + 128 * t3_nwg(gw); }   // producer, MMA issuer, epilogue warpgroups
 // epilogue unit width in columns: 64 where the GroupNorm width allows it (finer units = shorter accumulator
 // residency and tails, half the staging memory), 128 for GroupNorm width 128
 __host__ __device__ constexpr int t3_unit_cols(int gw) { return gw == 128 ? 128 : 64; }
@@ -81,10 +93,10 @@ __host__ __device__ inline T3Smem t3_smem_layout(int a_stage_bytes, int n_a, int
   s.a_ring = 0;
   s.b_ring = s.a_ring + n_a * a_stage_bytes;
   s.stage_out = s.b_ring + T3_NB * b_stage_bytes;
-  s.bars = s.stage_out + T3_NWG * t3_stage_out_bytes(gw);
+  s.bars = s.stage_out + t3_nwg(gw) * t3_stage_out_bytes(gw);
   s.params = s.bars + 512;
   s.scratch = s.params + 20 * cout_pad;                           // 16 B per channel (pairs) + 4 B bias
-  s.total = s.scratch + T3_NWG * 4 * S_t * ng * 8 + 1024 /*alignment slack*/;
+  s.total = s.scratch + t3_nwg(gw) * 4 * S_t * ng * 8 + 1024 /*alignment slack*/;
   return s;
 }
 
@@ -136,7 +148,7 @@ __device__ __forceinline__ f32x2 mish2(f32x2 y) {
 }
 
 template <int GW, int MH, int MODE, int NS>
-__global__ void __launch_bounds__(T3_THREADS, 1)
+__global__ void __launch_bounds__(t3_threads(GW), 1)
 conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmW2,
                const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO, const ConvT3Params p) {
@@ -144,7 +156,9 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   constexpr int CL = (MODE == T3_SINGLE) ? 1 : 2;
   constexpr int BN_ITEM = NS * T3_BN;                     // output channels per work item
   constexpr int ACC = 512 / BN_ITEM;                      // TMEM accumulator stages
-  constexpr int CW = DAD_T3_CW;                           // columns per TMEM load / epilogue chunk (8 or 16)
+  constexpr int CW = t3_cw(GW);                           // columns per TMEM load / epilogue chunk (8 or 16)
+  constexpr int T3_NWG = t3_nwg(GW);                      // epilogue warpgroups; each takes every T3_NWG-th unit
+  constexpr int T3_THREADS = t3_threads(GW);
   constexpr int UC = t3_unit_cols(GW);                    // columns per epilogue unit
   constexpr int UPI = BN_ITEM / UC;                       // units per whole item
   constexpr int UPH = (UPI > 1) ? UPI / 2 : 1;            // units per half entry (256-wide items only)

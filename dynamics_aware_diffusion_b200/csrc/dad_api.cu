@@ -562,7 +562,7 @@ cudaError_t set_t3_attr(int max_optin) {
 
 template <int GW, int MH, int MODE, int NS>
 int launch_t3(dad_handle *h, const ConvOp &op, const ConvT3Params &p, int grid, cudaStream_t st) {
-  cudaError_t e = launch_k(conv_t3_kernel<GW, MH, MODE, NS>, dim3((unsigned)grid), dim3(T3_THREADS), (size_t)op.t3_smem, st,
+  cudaError_t e = launch_k(conv_t3_kernel<GW, MH, MODE, NS>, dim3((unsigned)grid), dim3(t3_threads(GW)), (size_t)op.t3_smem, st,
                            MODE == T3_SINGLE ? 1 : 2, op.t3A1, op.t3A2, op.t3W, op.t3W2, op.t3R, op.t3O, p);
   if (e != cudaSuccess) DAD_FAIL(h, DAD_ERR_CUDA, "conv_t3 launch failed: %s", cudaGetErrorString(e));
   return DAD_OK;
