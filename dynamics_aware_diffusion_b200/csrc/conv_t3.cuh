@@ -30,23 +30,25 @@ constexpr int T3_BK = 64;
 #define DAD_T3_NB 6
 #endif
 constexpr int T3_NB = DAD_T3_NB;    // weight-tile ring (<= 8)
-// Epilogue shape per GroupNorm width, measured per layer: the C=512 layers (GW 64; also GW 128) are
-// MMA-bound and run best with 3 epilogue warpgroups reading 16 TMEM columns at a time; everything else is bound
-// by the epilogue's critical path -- an item of an L=32 layer has 4 units of work -- and gains 1-3 us per layer
-// from a 4th warpgroup, which fits the register file only with 8-column chunks.  -DDAD_T3_NWG / -DDAD_T3_CW force
-// one shape for every instantiation (experiments).
+// Epilogue shape per GroupNorm width, measured per layer.  The narrow Conv1dBlocks (GroupNorm width 16
+// or 32: C_out = 128 / 256) are bound by the epilogue's critical path -- an item of an L=32 layer is 4 units of
+// work -- and gain 1-3 us per layer from a 4th epilogue warpgroup, which fits the register file only with 8-column
+// TMEM chunks.  The wide, MMA-bound layers (GW 64 / 128) and the plain 1x1 convs (GW 0; up to K = 4096 for the
+// HalfCheetah skip projections, where the narrow chunks cost 30 us) keep 3 warpgroups x 16-column chunks.
+// -DDAD_T3_NWG / -DDAD_T3_CW force one shape for every instantiation (experiments).
+__host__ __device__ constexpr bool t3_narrow(int gw) { return gw == 16 || gw == 32; }
 __host__ __device__ constexpr int t3_nwg(int gw) {
 #ifdef DAD_T3_NWG
   return DAD_T3_NWG;
 #else
-  return (gw == 64 || gw == 128) ? 3 : 4;
+  return t3_narrow(gw) ? 4 : 3;
 #endif
 }
 __host__ __device__ constexpr int t3_cw(int gw) {
 #ifdef DAD_T3_CW
   return DAD_T3_CW;
 #else
-  return (gw == 64 || gw == 128) ? 16 : 8;
+  return t3_narrow(gw) ? 8 : 16;
 #endif
 }
 __host__ __device__ constexpr int t3_threads(int gw) { return 64 + 128 * t3_nwg(gw); }   // producer, MMA issuer, epilogue warpgroups
