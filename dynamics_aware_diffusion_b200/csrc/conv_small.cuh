@@ -2,11 +2,14 @@
 // (policies.py:193-223), so a layer is a 8..32-row GEMM against up to 2.6 MB of weights and the step is a chain of
 // 39 dependent launches.  The throughput kernels (conv_t3 / conv_tc) put such a layer on 2-4 CTAs and pay their
 // fixed cluster / TMEM / pipeline costs per launch; here a layer is spread over Cout/16 CTAs per sample:
-//   * CTA = 16 output channels of one sample.  Its weight slab ([16][taps*Cin] bf16, K-major rows as packed for the
-//     tensor-map path) is fetched by 1-D bulk copies issued BEFORE griddepcontrol.wait -- weights do not depend on
-//     the previous layer, so under programmatic dependent launch they stream in while that layer still runs.
+//   * CTA = 16 output channels of one sample (32 when a GroupNorm group is 256 wide, so that its cluster stays
+//     within 8 CTAs).  Its weight slab ([16][taps*Cin] bf16, K-major rows as packed for the tensor-map path) is
+//     fetched by a producer warp with 1-D bulk copies issued BEFORE griddepcontrol.wait -- weights do not depend
+//     on the previous layer, so under programmatic dependent launch they stream in while that layer still runs.
+//     A slab larger than shared memory (HalfCheetah / Door widths: up to 20 KB per weight row) goes through a
+//     3-stage ring of K chunks instead (full / empty mbarriers).
 //   * After the wait the haloed activation tile of the sample ((L_in + halo) rows x Cin) follows the same way.
-//   * 8 warps split K; each runs mma.sync.m16n8k16 (bf16 in, fp32 accumulate) with ldmatrix fragments straight
+//   * 8 consumer warps split K; each runs mma.sync.m16n8k16 (bf16 in, fp32 accumulate) with ldmatrix fragments straight
 //     from the padded rows (pitch = row bytes + 16 -> conflict-free), then the partial tiles are summed through
 //     shared memory.  tcgen05 would add TMEM allocation and a commit round trip to a GEMM of < 1 MFLOP per CTA.
 //   * Epilogue as in the throughput kernels: + bias, GroupNorm over (L x group) -- the group's CTAs form a

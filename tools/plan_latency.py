@@ -19,7 +19,7 @@ for lat in (0, 8):
     pol = DynamicsAwarePolicy(dif, projection_matrix=P, normalizer=nz, state_dim=w["n"], observation_dim=w["n"],
                               action_dim=w["m"], horizon=w["H"], projection_schedule="noise_schedule", projection_strength=1.0)
     start = torch.zeros(1, T, device=dev)
-    for B in (1, 2, 4, 8):
+    for B in (1, 4):
         ts = []
         for k in range(4):
             torch.cuda.synchronize()
