@@ -4,7 +4,9 @@ import os
 
 from .build import LIB_PATH as _DEFAULT_LIB
 
-LIB_PATH = os.environ.get("DAD_LIB_PATH", _DEFAULT_LIB)      # tuning variants only; default = the in-tree build
+# The in-tree build is THE library.  A tuning variant (build.py --out=...) is picked up only when DAD_TUNING=1 is set
+# alongside DAD_LIB_PATH, so a stray variable cannot swap the kernels under a production process.
+LIB_PATH = (os.environ.get("DAD_LIB_PATH", _DEFAULT_LIB) if os.environ.get("DAD_TUNING") == "1" else _DEFAULT_LIB)
 
 DAD_ABI_VERSION = 1
 DAD_MAX_LEVELS = 8
@@ -19,6 +21,7 @@ EXPORTS = (
     "dad_loop_begin", "dad_loop_unet", "dad_loop_step", "dad_graph_epoch", "dad_loop_replayed",
     "dad_build_projection_matrix",
     "dad_sample_profile", "dad_layer_count", "dad_layer_info", "dad_time_layer", "dad_time_step_kernel",
+    "dad_set_fusion", "dad_unit_count", "dad_unit_info", "dad_time_unit",
 )
 
 
@@ -45,6 +48,12 @@ class DadLayerDesc(ctypes.Structure):
     _fields_ = [("name", ctypes.c_char * 96), ("L_out", ctypes.c_int32), ("C_in", ctypes.c_int32),
                 ("C_out", ctypes.c_int32), ("taps", ctypes.c_int32), ("tile_n", ctypes.c_int32),
                 ("group_width", ctypes.c_int32), ("flops_per_sample", ctypes.c_int64), ("kernel", ctypes.c_char * 64)]
+
+
+class DadUnitDesc(ctypes.Structure):
+    _fields_ = [("first_layer", ctypes.c_int32), ("n_layers", ctypes.c_int32), ("is_chain", ctypes.c_int32),
+                ("L_out", ctypes.c_int32), ("C_out", ctypes.c_int32), ("flops_per_sample", ctypes.c_int64),
+                ("kernel", ctypes.c_char * 64)]
 
 
 class DadError(RuntimeError):
@@ -100,6 +109,10 @@ def lib():
     L.dad_layer_info.argtypes = [vp, i32, ctypes.POINTER(DadLayerDesc)]
     L.dad_time_layer.argtypes = [vp, i32, i32, i32, ctypes.POINTER(ctypes.c_float), vp]
     L.dad_time_step_kernel.argtypes = [vp, i32, i32, u32, i32, ctypes.POINTER(ctypes.c_float), vp]
+    L.dad_set_fusion.argtypes = [vp, i32]
+    L.dad_unit_count.argtypes = [vp]
+    L.dad_unit_info.argtypes = [vp, i32, ctypes.POINTER(DadUnitDesc)]
+    L.dad_time_unit.argtypes = [vp, i32, i32, i32, ctypes.POINTER(ctypes.c_float), vp]
     if L.dad_abi_version() != DAD_ABI_VERSION:
         raise RuntimeError("libdad_b200.so ABI %d != binding ABI %d; rebuild" % (L.dad_abi_version(), DAD_ABI_VERSION))
     _lib = L

@@ -6,6 +6,16 @@
 
 namespace dad {
 
+// Kernel-side ablation bits (skip the epilogue arithmetic, the MMAs, ...) and cycle counters are compiled in only
+// with -DDAD_TUNING; in the shipping build the expressions are constants and the branches disappear.
+#ifdef DAD_TUNING
+#define DAD_DEBUG_BITS(p) ((p).debug)
+#define DAD_PROF_PTR(p) ((p).prof)
+#else
+#define DAD_DEBUG_BITS(p) 0
+#define DAD_PROF_PTR(p) (static_cast<unsigned long long *>(nullptr))
+#endif
+
 constexpr int kMaxTaps = 8;
 constexpr int kMaxCond = 8;
 constexpr int kGroups = 8;          // nn.GroupNorm(8, C), temporal_unet.py:67
@@ -27,6 +37,7 @@ struct LoopState {
   unsigned long long seed;
   unsigned long long sample_offset;  // global index of row 0 of this chunk (Philox subsequence)
   const long long *t_rows;  // per-row timesteps for a stand-alone forward, or nullptr (uniform `step`)
+  int n_table;              // rows of the time tables: per-row timesteps are clamped to [0, n_table) on the device
   // conditions (GuidedPolicy.apply_conditions)
   int n_cond;
   int cond_per_batch;

@@ -21,6 +21,7 @@
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
+#include "f32x2.cuh"
 
 namespace dad {
 
@@ -100,53 +101,6 @@ __host__ __device__ inline T3Smem t3_smem_layout(int a_stage_bytes, int n_a, int
   s.scratch = s.params + 20 * cout_pad;                           // 16 B per channel (pairs) + 4 B bias
   s.total = s.scratch + t3_nwg(gw) * 4 * S_t * ng * 8 + 1024 /*alignment slack*/;
   return s;
-}
-
-// ---- packed fp32x2 helpers (sm_100 FFMA2 / FADD2 / FMUL2) ---------------------------------------------
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void upk2(f32x2 v, float &lo, float &hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// Mish on a pair: y * (1 - 2 / ((1 + e^y)^2 + 1))
-__device__ __forceinline__ f32x2 mish2(f32x2 y) {
-  float z0, z1;
-  upk2(fmul2(y, pk2(1.4426950408889634f, 1.4426950408889634f)), z0, z1);
-  const f32x2 one = pk2(1.f, 1.f);
-  const f32x2 u = fadd2(pk2(ex2_approx(z0), ex2_approx(z1)), one);
-  float w0, w1;
-  upk2(ffma2(u, u, one), w0, w1);
-  const f32x2 t = ffma2(pk2(rcp_approx(w0), rcp_approx(w1)), pk2(-2.f, -2.f), one);
-  return fmul2(y, t);
 }
 
 template <int GW, int MH, int MODE, int NS>
@@ -286,7 +240,7 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   // assume per-lane operands and wraps every UTMALDG / UTCHMMA in an elect-broadcast loop of ~20 instructions.)
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (!(p.debug & 2)) {
+    if (!(DAD_DEBUG_BITS(p) & 2)) {
       const bool leader_lane = ptx::elect_one();
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
@@ -307,7 +261,7 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           const CUtensorMap *am = (ch < p.kch1) ? &tmA1 : &tmA2;
           const int c0 = (ch < p.kch1 ? ch : ch - p.kch1) * T3_BK;
           if (leader_lane) {
-            if (p.debug & 64) {
+            if (DAD_DEBUG_BITS(p) & 64) {
               if (MODE != T3_PAIR || cta_rank == 0) ptx::mbar_arrive(&full_a[sa]);   // profiling: MMAs without TMA
             } else if constexpr (MODE == T3_PAIR) {
               if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_a[sa], 2u * (uint32_t)p.a_tx_bytes);
@@ -323,7 +277,7 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             uint8_t *wdst = smem + lay.b_ring + sb * p.b_stage_bytes;
             const int k0 = (t * kch + ch) * T3_BK;
             if (!leader_lane) {
-            } else if (p.debug & 64) {
+            } else if (DAD_DEBUG_BITS(p) & 64) {
               if (MODE != T3_PAIR || cta_rank == 0) ptx::mbar_arrive(&full_b[sb]);
             } else if constexpr (MODE == T3_SINGLE) {
               ptx::mbar_arrive_expect_tx(&full_b[sb], (uint32_t)p.b_stage_bytes);
@@ -360,7 +314,7 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const uint32_t tap_step = p.taps > 1 ? (uint32_t)(p.tap_row[1] - p.tap_row[0]) * 8u : 0u;   // rows * 128 B >> 4
       const uint32_t tap_first = (uint32_t)p.tap_row[0] * 8u;
       const int n_taps = p.taps, n_a = p.n_a_stages;
-      const bool run = !(p.debug & 2);
+      const bool run = !(DAD_DEBUG_BITS(p) & 2);
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       int it = 0;
@@ -502,7 +456,7 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       int it, item, ns, acol;
       bool half;
       if (!unit(u, it, item, ns, acol, half)) break;
-      if (p.prof) pc_t0 = clock64();
+      if (DAD_PROF_PTR(p)) pc_t0 = clock64();
       const int gm = item / n_tiles_n, tn = item - gm * n_tiles_n;
       const int tm = gm * CL + (int)cta_rank;
       const int b0 = tm * p.S_t;
@@ -519,8 +473,8 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll
       for (int h = 0; h < MH; ++h) t_addr[h] = tmem_base + ((it * MH + h) % ACC) * BN_ITEM + ((uint32_t)(q * 32) << 16);
       ptx::tc_fence_after();
-      if (p.prof) { pc_t1 = clock64(); pc_wait += pc_t1 - pc_t0; pc_t0 = pc_t1; }
-      if ((p.debug & 1) || !tile_ok) {
+      if (DAD_PROF_PTR(p)) { pc_t1 = clock64(); pc_wait += pc_t1 - pc_t0; pc_t0 = pc_t1; }
+      if ((DAD_DEBUG_BITS(p) & 1) || !tile_ok) {
         // nothing to write for this super-tile: consume the residual that was prefetched for it and move on
         if (p.has_res) { ptx::mbar_wait(&res_bar[wg], res_phase); res_phase ^= 1; }
 #pragma unroll
@@ -589,7 +543,7 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         // before it prefetched this unit's residual (or checks it here when there is none)
         if (!p.has_res && elected) ptx::bulk_wait_read0();
         ptx::named_bar_sync(1 + wg, 128);          // statistics exchanged, staging buffer reusable
-        if (p.prof) { pc_t1 = clock64(); pc_p1 += pc_t1 - pc_t0; pc_t0 = pc_t1; }
+        if (DAD_PROF_PTR(p)) { pc_t1 = clock64(); pc_p1 += pc_t1 - pc_t0; pc_t0 = pc_t1; }
 
         // ---- pass 2: normalise, Mish, (+ time bias | + residual), convert, stage, TMA store
 #pragma unroll 1
@@ -638,7 +592,7 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll
               for (int j = 0; j < CW / 2; ++j) {
                 const f32x2 xn = ffma2(pk2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), a2[j], bsh[j]);
-                y[j] = fadd2((p.debug & 32) ? xn : mish2(xn), tt2[j]);
+                y[j] = fadd2((DAD_DEBUG_BITS(p) & 32) ? xn : mish2(xn), tt2[j]);
               }
             } else {
               f32x2 bb[CW / 2];
@@ -685,7 +639,7 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           if (nx_h == MH) { nx_h = 0; nx_ns = nns; nx_item = nitem; }
           const bool same_item = (h + 1 < MH);
           if (elected) {
-            if (!(p.debug & 4)) {
+            if (!(DAD_DEBUG_BITS(p) & 4)) {
               ptx::tma_store_3d(&tmO, stg, n0, b0, h * pos_per_half);
               if constexpr (UC == 128) ptx::tma_store_3d(&tmO, stg + 16384, n0 + 64, b0, h * pos_per_half);
             }
@@ -703,14 +657,14 @@ conv_t3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           }
         }
       }
-      if (p.prof) { pc_p2 += clock64() - pc_t0; pc_n += 1; }
+      if (DAD_PROF_PTR(p)) { pc_p2 += clock64() - pc_t0; pc_n += 1; }
     }
     if (elected) ptx::bulk_wait0();               // all stores of this warpgroup have landed before the CTA exits
-    if (p.prof && lane == 0) {
-      atomicAdd(p.prof + 0, (unsigned long long)pc_wait);
-      atomicAdd(p.prof + 1, (unsigned long long)pc_p1);
-      atomicAdd(p.prof + 2, (unsigned long long)pc_p2);
-      atomicAdd(p.prof + 3, (unsigned long long)pc_n);
+    if (DAD_PROF_PTR(p) && lane == 0) {
+      atomicAdd(DAD_PROF_PTR(p) + 0, (unsigned long long)pc_wait);
+      atomicAdd(DAD_PROF_PTR(p) + 1, (unsigned long long)pc_p1);
+      atomicAdd(DAD_PROF_PTR(p) + 2, (unsigned long long)pc_p2);
+      atomicAdd(DAD_PROF_PTR(p) + 3, (unsigned long long)pc_n);
     }
   }
 

@@ -159,7 +159,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0 && !(p.debug & 2)) {
+    if (lane == 0 && !(DAD_DEBUG_BITS(p) & 2)) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -192,7 +192,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);   // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < ((p.debug & 2) ? 0 : num_kb); ++kb) {
+        for (int kb = 0; kb < ((DAD_DEBUG_BITS(p) & 2) ? 0 : num_kb); ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);      // TMA bytes have landed
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -231,7 +231,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     int it = wg;
     long long pc_wait = 0, pc_p1 = 0, pc_p2 = 0, pc_n = 0, pc_t0 = 0, pc_t1 = 0;
     for (int tile = blockIdx.x + wg * gridDim.x; tile < total_tiles; tile += TC_EPI_WG * gridDim.x, it += TC_EPI_WG) {
-      if (p.prof) pc_t0 = clock64();
+      if (DAD_PROF_PTR(p)) pc_t0 = clock64();
       const int tm = tile / p.n_tiles_n, tn = tile - tm * p.n_tiles_n;
       const int n0 = tn * BN;
       const int b = tm * spt + s_in_tile;
@@ -241,7 +241,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const uint32_t t_addr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
       const size_t orow = ((size_t)b * L_total + (size_t)l * p.out_mul + p.out_phase) * p.Cout + n0;
       // residual of the first column chunk: requested before the accumulator is even ready
-      const bool has_res = (p.residual != nullptr) && valid && !p.out_f32 && !(p.debug & 8);
+      const bool has_res = (p.residual != nullptr) && valid && !p.out_f32 && !(DAD_DEBUG_BITS(p) & 8);
       uint4 rcur[CW / 8];
       if (has_res) {
         const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + orow);
@@ -250,8 +250,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       }
       ptx::mbar_wait(&tfull_bar[as], aphase);
       ptx::tc_fence_after();
-      if (p.prof) { pc_t1 = clock64(); pc_wait += pc_t1 - pc_t0; pc_t0 = pc_t1; }
-      if (p.debug == 1) {
+      if (DAD_PROF_PTR(p)) { pc_t1 = clock64(); pc_wait += pc_t1 - pc_t0; pc_t0 = pc_t1; }
+      if (DAD_DEBUG_BITS(p) == 1) {
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
@@ -259,7 +259,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       }
 
       float mean_a[NG], rstd_a[NG];               // dynamically indexed -> thread-local memory (L1 resident)
-      if (p.debug & 16) {
+      if (DAD_DEBUG_BITS(p) & 16) {
 #pragma unroll
         for (int g = 0; g < NG; ++g) { mean_a[g] = 0.f; rstd_a[g] = 1.f; }
       } else if constexpr (GW > 0) {
@@ -329,10 +329,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         }
       }
 
-      if (p.prof) { pc_t1 = clock64(); pc_p1 += pc_t1 - pc_t0; pc_t0 = pc_t1; }
+      if (DAD_PROF_PTR(p)) { pc_t1 = clock64(); pc_p1 += pc_t1 - pc_t0; pc_t0 = pc_t1; }
       // ---- pass 2: normalise, Mish, (+ time bias | + residual), convert, store
       const float *trow = nullptr;
-      if (rows_t) trow = p.ttab + (size_t)(valid ? t_rows[b] : 0) * p.Cout + n0;
+      if (rows_t) {
+        // clamped: an out-of-range timestep must not read outside the table (the Python wrapper rejects it with an error)
+        const long long tr = valid ? t_rows[b] : 0;
+        trow = p.ttab + (size_t)min(max(tr, 0ll), (long long)p.ls->n_table - 1) * p.Cout + n0;
+      }
 #pragma unroll 1
       for (int c = 0; c < NCHUNK; ++c) {
         uint32_t v[32];
@@ -368,7 +372,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < CW; ++j) {
             const float xn = fmaf(__uint_as_float(v[j]), a[j], bsh[j]);
-            y[j] = ((p.debug & 32) ? xn : mish_tc(xn)) + tt[j];
+            y[j] = ((DAD_DEBUG_BITS(p) & 32) ? xn : mish_tc(xn)) + tt[j];
           }
           if (trow) {
 #pragma unroll
@@ -385,7 +389,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < CW; ++j) y[j] = __uint_as_float(v[j]) + bb[j];
         }
-        if (valid && (!(p.debug & 4) || y[0] == 123.456f)) {
+        if (valid && (!(DAD_DEBUG_BITS(p) & 4) || y[0] == 123.456f)) {
           if (p.proj_x) {
             // dynamics projector: y = x' + alpha (N x' + q), Diffuser-style inpainting, optional trace (policies.py:409-485,61-62)
             const LoopState &ls = *p.ls;
@@ -444,13 +448,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
-      if (p.prof) { pc_p2 += clock64() - pc_t0; pc_n += 1; }
+      if (DAD_PROF_PTR(p)) { pc_p2 += clock64() - pc_t0; pc_n += 1; }
     }
-    if (p.prof && lane == 0) {
-      atomicAdd(p.prof + 0, (unsigned long long)pc_wait);
-      atomicAdd(p.prof + 1, (unsigned long long)pc_p1);
-      atomicAdd(p.prof + 2, (unsigned long long)pc_p2);
-      atomicAdd(p.prof + 3, (unsigned long long)pc_n);
+    if (DAD_PROF_PTR(p) && lane == 0) {
+      atomicAdd(DAD_PROF_PTR(p) + 0, (unsigned long long)pc_wait);
+      atomicAdd(DAD_PROF_PTR(p) + 1, (unsigned long long)pc_p1);
+      atomicAdd(DAD_PROF_PTR(p) + 2, (unsigned long long)pc_p2);
+      atomicAdd(DAD_PROF_PTR(p) + 3, (unsigned long long)pc_n);
     }
   }
 

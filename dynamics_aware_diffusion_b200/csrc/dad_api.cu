@@ -17,6 +17,9 @@
 #include "common.cuh"
 #include "conv_tc.cuh"
 #include "conv_t3.cuh"
+#include "conv_chain.cuh"
+#include "chain_host.h"
+#include "launch.cuh"
 #include "conv_small.cuh"
 #include "kernels_f32.cuh"
 #include "step_kernel.cuh"
@@ -59,6 +62,8 @@ struct ConvOp {
   int t3_MH = 1, t3_mode = 0, t3_NS = 1, t3_smem = 0;
   CUtensorMap t3A1, t3A2, t3W, t3W2, t3R, t3O;
   ConvT3Params t3p{};
+  // chain path (conv_chain.cuh): index of the launch unit this conv belongs to, or -1
+  int chain = -1;
   // small-batch latency path (conv_small.cuh)
   bool small = false;
   int sm_mt = 1, sm_nt = 2, sm_cluster = 1, sm_smem = 0;
@@ -69,6 +74,21 @@ struct TimeBlock {
   std::string stem;   // "<block>.time_mlp.1"
   int C = 0;
   float *tab = nullptr;  // [S][C]
+};
+
+// One launch of conv_chain_kernel: consecutive stride-1 convolutions of one U-Net level (same length, width and
+// GroupNorm shape), or a single one.
+struct ChainUnit {
+  std::vector<int> ops;             // indices into dad_handle::ops, in execution order
+  int GW = 0, MH = 1, NS = 1, L = 0, S_t = 0;
+  int smem = 0, max_clusters = 0;
+  ChainArgs args{};
+};
+
+// What enqueue_unet walks: a chain (index into dad_handle::chains) or a single op on the generic kernels.
+struct LaunchUnit {
+  int chain = -1;
+  int op = -1;
 };
 
 struct GraphEntry {
@@ -130,6 +150,14 @@ struct dad_handle {
   long long counting = 0;            // kernels enqueued since last reset (capture accounting)
   EncodeTiledFn encode = nullptr;
   int64_t conv_flops = 0;
+  // conv chains: 0 = one launch per conv (round-1 kernels), 1 = chain kernel without fusion, 2 = one launch per
+  // ResidualTemporalBlock, 3 = one launch per run of blocks of a level
+  int fusion = 3;
+  std::vector<ChainUnit> chains;
+  std::vector<LaunchUnit> units;
+  unsigned *d_flags = nullptr;       // [ops][tiles_cap] tile-completion counters, zeroed by stage_x_kernel every pass
+  int tiles_cap = 0;
+  unsigned *d_err = nullptr;
 };
 
 namespace {
@@ -159,6 +187,37 @@ int dev_alloc(dad_handle *h, T **p, size_t n) {
   return DAD_OK;
 }
 
+// Replace *p by a larger allocation; the old buffer is released (the caller has made sure nothing reads it any more).
+template <typename T>
+int dev_regrow(dad_handle *h, T **p, size_t n) {
+  T *old = *p;
+  int rc = dev_alloc(h, p, n);
+  if (rc) return rc;
+  if (old) {
+    auto it = std::find(h->allocs.begin(), h->allocs.end(), (void *)old);
+    if (it != h->allocs.end()) h->allocs.erase(it);
+    cudaFree(old);
+  }
+  return DAD_OK;
+}
+
+// Set-up entry points rewrite device tables (weights, schedule, projector, conditions) that sampling work still in
+// flight on ANY stream may be reading: they first wait for the device to go idle.
+#define DAD_QUIESCE(h) CK(h, cudaDeviceSynchronize())
+
+// Temporaries of a set-up call, released on every return path.
+struct DevTemps {
+  std::vector<void *> v;
+  ~DevTemps() { for (void *p : v) cudaFree(p); }
+  template <typename T>
+  cudaError_t alloc(T **p, size_t n) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(n * sizeof(T), 16));
+    if (e == cudaSuccess) { v.push_back(q); *p = reinterpret_cast<T *>(q); }
+    return e;
+  }
+};
+
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // Set-up copy (host or device source) that has fully landed when the call returns.  A plain cudaMemcpy from
@@ -175,41 +234,6 @@ inline cudaError_t copy_now(void *dst, const void *src, size_t bytes, cudaStream
   cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st);
   if (e != cudaSuccess) return e;
   return cudaStreamSynchronize(st);
-}
-
-// Every kernel of the sampling step is launched with programmatic stream serialization: it may start (and run
-// its set-up) while its predecessor drains, and calls griddepcontrol.wait before touching global data.
-// DAD_PDL=0 disables the attribute (plain stream order).
-inline bool pdl_enabled() {
-  static const bool on = !(getenv("DAD_PDL") && atoi(getenv("DAD_PDL")) == 0);
-  return on;
-}
-
-template <typename... KArgs, typename... Args>
-cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
-                     Args &&...args) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute at[2];
-  int n = 0;
-  if (cluster > 1) {
-    at[n].id = cudaLaunchAttributeClusterDimension;
-    at[n].val.clusterDim.x = (unsigned)cluster;
-    at[n].val.clusterDim.y = 1;
-    at[n].val.clusterDim.z = 1;
-    ++n;
-  }
-  if (pdl_enabled()) {
-    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[n].val.programmaticStreamSerializationAllowed = 1;
-    ++n;
-  }
-  cfg.attrs = at;
-  cfg.numAttrs = (unsigned)n;
-  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
 int new_act(dad_handle *h, int L, int C) {
@@ -428,7 +452,7 @@ int setup_tc_op(dad_handle *h, ConvOp &op) {
     p.tap_j[t] = (off - ph) / s;
   }
   p.out_f32 = op.head ? 1 : 0;
-  p.debug = getenv("DAD_TC_DEBUG") ? atoi(getenv("DAD_TC_DEBUG")) : 0;
+  p.debug = tuning_env("DAD_TC_DEBUG", 0);
   p.prof = nullptr;
   p.ls = h->d_ls;
   return DAD_OK;
@@ -478,7 +502,7 @@ int make_t3_act_tmap(dad_handle *h, CUtensorMap *m, int act, int box_s, int box_
 
 bool t3_eligible(const dad_handle *h, const ConvOp &op) {
   const ConvGeom &g = op.g;
-  if (getenv("DAD_T3") && atoi(getenv("DAD_T3")) == 0) return false;
+  if (tuning_env("DAD_T3", 1) == 0) return false;
   if (op.head || op.transposed || g.in_stride != 1 || g.out_mul != 1) return false;
   if (g.Cout % T3_BN || g.C1 % 64 || g.C2 % 64) return false;
   if (!(g.L_out == 4 || g.L_out == 8 || g.L_out == 16 || g.L_out == 32)) return false;
@@ -510,13 +534,13 @@ int setup_t3_op(dad_handle *h, ConvOp &op) {
   p.kch2 = g.C2 / 64;
   p.taps = g.taps;
   p.has_res = op.res >= 0 ? 1 : 0;
-  p.debug = getenv("DAD_TC_DEBUG") ? atoi(getenv("DAD_TC_DEBUG")) : 0;
+  p.debug = tuning_env("DAD_TC_DEBUG", 0);
   p.prof = nullptr;
   p.ls = h->d_ls;
   // cooperation mode: CTA pairs (cta_group::2) by default, 256-wide items where the layer allows it
-  op.t3_mode = getenv("DAD_T3_MODE") ? atoi(getenv("DAD_T3_MODE")) : T3_PAIR;
+  op.t3_mode = tuning_env("DAD_T3_MODE", T3_PAIR);
   if (op.t3_mode < 0 || op.t3_mode > 2) op.t3_mode = T3_PAIR;
-  const int want_ns = getenv("DAD_T3_NS") ? atoi(getenv("DAD_T3_NS")) : 2;
+  const int want_ns = tuning_env("DAD_T3_NS", 2);
   op.t3_NS = (op.t3_mode == T3_PAIR && op.t3_MH == 1 && g.Cout % 256 == 0 && want_ns == 2) ? 2 : 1;
   p.n_tiles_n = g.Cout / (T3_BN * op.t3_NS);
   p.b_stage_bytes = op.t3_mode == T3_PAIR ? op.t3_NS * 8192 : 16384;
@@ -590,6 +614,223 @@ int enqueue_t3(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
   if (rc == DAD_ERR_INVALID) DAD_FAIL(h, DAD_ERR_INVALID, "internal: no conv_t3 instantiation for GW=%d MH=%d mode=%d NS=%d", op.GW, op.t3_MH, op.t3_mode, op.t3_NS);
   h->counting += 1;
   return rc;
+}
+
+// ---- conv chains (conv_chain.cuh) -------------------------------------------------------------------
+// A stride-1 conv qualifies when the CTA-pair kernel can run it: whole 128-column tiles, 64-channel K blocks, a
+// sequence length that packs whole samples into 128-row half tiles, and a GroupNorm width the epilogue implements
+// (a plain 1x1 residual conv borrows the width of its block: same C_out).
+struct ChainShape {
+  int GW, MH, NS, S_t;
+};
+
+bool chain_shape(const dad_handle *h, const ConvOp &op, ChainShape *out) {
+  const ConvGeom &g = op.g;
+  if (!h->bf16 || op.head || op.transposed || g.in_stride != 1 || g.out_mul != 1) return false;
+  if (g.Cout % CH_BN || g.C1 % 64 || g.C2 % 64 || g.Cout % kGroups) return false;
+  if (!(g.L_out == 4 || g.L_out == 8 || g.L_out == 16 || g.L_out == 32)) return false;
+  const int gw = g.Cout / kGroups;
+  if (!(gw == 16 || gw == 32 || gw == 64 || gw == 128 || gw == 256)) return false;
+  ChainShape s;
+  s.GW = gw;
+  s.MH = g.L_out == 32 ? 2 : 1;
+  s.NS = (s.MH == 1 && g.Cout % 256 == 0) ? 2 : 1;
+  s.S_t = 128 * s.MH / g.L_out;
+  if (gw == 256 && s.NS != 2) return false;       // a 256-column group needs 256-wide items (L <= 16)
+  *out = s;
+  return true;
+}
+
+// "downs.0.1.blocks.0.block.0.weight" / "downs.0.1.residual_conv.weight" -> "downs.0.1": the ResidualTemporalBlock
+std::string block_stem(const ConvOp &op) {
+  size_t pos = op.wname.find(".blocks.");
+  if (pos == std::string::npos) pos = op.wname.find(".residual_conv");
+  if (pos == std::string::npos) pos = op.wname.find(".block.");
+  return pos == std::string::npos ? op.wname : op.wname.substr(0, pos);
+}
+
+// Shared memory and ring depths of a chain; false when even the smallest configuration does not fit.
+bool chain_config(const dad_handle *h, ChainUnit &cu) {
+  int a_stage = 0;
+  for (int oi : cu.ops) {
+    const ConvGeom &g = h->ops[oi].g;
+    int lo = 0, hi = 0;
+    for (int t = 0; t < g.taps; ++t) { lo = std::min(lo, g.tap_off[t]); hi = std::max(hi, g.tap_off[t]); }
+    const int bytes = (cu.L + hi - lo) * cu.S_t * 128;
+    a_stage = std::max(a_stage, (bytes + 1023) / 1024 * 1024);
+  }
+  const int b_stage = cu.NS * 8192;
+  // deepest weight ring first (the MMA issue rate depends on it), then as many activation stages as still fit
+  static const int combos[][2] = {{4, 6}, {3, 6}, {2, 6}, {3, 5}, {2, 5}, {3, 4}, {2, 4}, {2, 3}};
+  for (auto &c : combos) {
+    const ChSmem lay = ch_smem_layout(a_stage, c[0], b_stage, c[1], cu.S_t, cu.GW);
+    if (lay.total <= h->max_smem_optin) {
+      ChainParams &p = cu.args.p;
+      p.a_stage_bytes = a_stage;
+      p.n_a_stages = c[0];
+      p.b_stage_bytes = b_stage;
+      p.nb_stages = c[1];
+      cu.smem = lay.total;
+      return true;
+    }
+  }
+  return false;
+}
+
+// Tensor maps, scalars and dependency counters of every conv of the chain.
+int finish_chain(dad_handle *h, ChainUnit &cu, int unit_index) {
+  const int UC = ch_unit_cols(cu.GW);
+  ChainParams &p = cu.args.p;
+  p.ls = h->d_ls;
+  p.err = h->d_err;
+  p.n_convs = (int)cu.ops.size();
+  p.flag_epoch = 1;
+  p.L = cu.L;
+  p.S_t = cu.S_t;
+  p.n_tiles_n = h->ops[cu.ops[0]].g.Cout / (CH_BN * cu.NS);
+  p.debug = 0;
+  // which act is produced by which conv of this chain
+  std::map<int, int> producer;
+  for (size_t k = 0; k < cu.ops.size(); ++k) producer[h->ops[cu.ops[k]].out] = (int)k;
+  std::vector<bool> consumed(cu.ops.size(), false);
+  for (size_t k = 0; k < cu.ops.size(); ++k) {
+    ConvOp &op = h->ops[cu.ops[k]];
+    const ConvGeom &g = op.g;
+    ChainConv &cv = cu.args.convs[k];
+    ChainConvMeta &m = cv.m;
+    int lo = 0, hi = 0;
+    for (int t = 0; t < g.taps; ++t) { lo = std::min(lo, g.tap_off[t]); hi = std::max(hi, g.tap_off[t]); }
+    const int box_l = cu.L + hi - lo;
+    int rc;
+    if ((rc = make_t3_act_tmap(h, &cv.tmA1, op.in1, cu.S_t, box_l, "chain activation"))) return rc;
+    if ((rc = make_t3_act_tmap(h, &cv.tmA2, op.in2 >= 0 ? op.in2 : op.in1, cu.S_t, box_l, "chain activation 2"))) return rc;
+    const cuuint64_t K = (cuuint64_t)g.taps * op.Cin_store;
+    cuuint64_t dims[2] = {K, (cuuint64_t)op.Cout_pad};
+    cuuint64_t strides[1] = {K * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)(64 * cu.NS)};         // each CTA of the pair keeps half of the item's rows
+    if ((rc = make_tmap_raw(h, &cv.tmW, op.w_b16, 2, dims, strides, box, "chain weights"))) return rc;
+    const int pph = 128 / cu.S_t;
+    if ((rc = make_t3_act_tmap(h, &cv.tmO, op.out, cu.S_t, pph, "chain output"))) return rc;
+    if ((rc = make_t3_act_tmap(h, &cv.tmR, op.res >= 0 ? op.res : op.out, cu.S_t, pph, "chain residual"))) return rc;
+    m.bias = op.bias;
+    m.gamma = op.gamma;
+    m.beta = op.beta;
+    m.ttab = op.tblock >= 0 ? h->tblocks[op.tblock].tab : nullptr;
+    m.Cout = g.Cout;
+    m.kch1 = g.C1 / 64;
+    m.kch2 = g.C2 / 64;
+    m.taps = g.taps;
+    m.halo_lo = -lo;
+    m.tap_first = (g.tap_off[0] - lo) * cu.S_t * 8;              // rows * 128 B in 16-byte units
+    m.tap_step = g.taps > 1 ? (g.tap_off[1] - g.tap_off[0]) * cu.S_t * 8 : 0;
+    for (int t = 2; t < g.taps; ++t)
+      if (g.tap_off[t] - g.tap_off[t - 1] != g.tap_off[1] - g.tap_off[0])
+        DAD_FAIL(h, DAD_ERR_INVALID, "internal: chain conv %s has unevenly spaced taps", op.wname.c_str());
+    m.a_tx_bytes = box_l * cu.S_t * 128;
+    m.has_res = op.res >= 0 ? 1 : 0;
+    m.plain = op.gname.empty() ? 1 : 0;
+    m.flag_out = nullptr;
+    m.flag_a = nullptr;
+    m.flag_r = nullptr;
+    m.need_a = m.need_r = 0;
+    auto dep = [&](int act, const unsigned **flag, int *need) {
+      auto it = producer.find(act);
+      if (act < 0 || it == producer.end() || it->second >= (int)k) return;
+      const ConvOp &src = h->ops[cu.ops[it->second]];
+      *flag = h->d_flags + (size_t)cu.ops[it->second] * h->tiles_cap;
+      *need = (src.g.Cout / UC) * cu.MH;                          // stores that complete one tile of the producer
+      consumed[it->second] = true;
+    };
+    dep(op.in1, &m.flag_a, &m.need_a);
+    dep(op.res, &m.flag_r, &m.need_r);
+    if (op.in2 >= 0 && producer.count(op.in2) && producer[op.in2] < (int)k)
+      DAD_FAIL(h, DAD_ERR_INVALID, "internal: chain conv %s takes its second source from the same chain", op.wname.c_str());
+    op.chain = unit_index;
+  }
+  for (size_t k = 0; k < cu.ops.size(); ++k)
+    if (consumed[k]) cu.args.convs[k].m.flag_out = h->d_flags + (size_t)cu.ops[k] * h->tiles_cap;
+  const ChainOps *ops = chain_ops(cu.GW);
+  CK(h, ops->prepare(cu.MH, cu.NS, h->max_smem_optin));
+  CK(h, ops->max_clusters(cu.MH, cu.NS, cu.smem, &cu.max_clusters));
+  cu.max_clusters = std::min(cu.max_clusters, h->sm_count / 2);
+  if (cu.max_clusters < 1) DAD_FAIL(h, DAD_ERR_CUDA, "conv_chain_kernel<GW=%d> cannot be resident with %d bytes of shared memory", cu.GW, cu.smem);
+  return DAD_OK;
+}
+
+// Partition the plan into launch units for the current fusion level.
+int build_units(dad_handle *h) {
+  h->chains.clear();
+  h->units.clear();
+  for (ConvOp &op : h->ops) op.chain = -1;
+  ChainUnit cur;
+  std::string cur_block;
+  auto flush = [&]() {
+    if (cur.ops.empty()) return;
+    LaunchUnit lu;
+    lu.chain = (int)h->chains.size();
+    h->chains.push_back(cur);
+    h->units.push_back(lu);
+    cur = ChainUnit();
+  };
+  for (size_t i = 0; i < h->ops.size(); ++i) {
+    const ConvOp &op = h->ops[i];
+    ChainShape sh;
+    if (h->fusion >= 1 && chain_shape(h, op, &sh)) {
+      const std::string blk = block_stem(op);
+      bool join = !cur.ops.empty() && h->fusion >= 2 && (int)cur.ops.size() < CH_MAX_CONVS && cur.L == op.g.L_out &&
+                  cur.GW == sh.GW && cur.MH == sh.MH && cur.NS == sh.NS &&
+                  h->ops[cur.ops[0]].g.Cout == op.g.Cout && (h->fusion >= 3 || blk == cur_block);
+      if (join) {
+        // the second source (a skip tensor) must come from an earlier launch
+        for (int oi : cur.ops) if (h->ops[oi].out == op.in2) join = false;
+      }
+      if (join) {
+        ChainUnit trial = cur;
+        trial.ops.push_back((int)i);
+        if (!chain_config(h, trial)) join = false; else cur = trial;
+      }
+      if (!join) {
+        flush();
+        cur.ops.push_back((int)i);
+        cur.GW = sh.GW; cur.MH = sh.MH; cur.NS = sh.NS; cur.L = op.g.L_out; cur.S_t = sh.S_t;
+        if (!chain_config(h, cur)) {        // does not fit at all: generic kernel
+          cur = ChainUnit();
+          LaunchUnit lu;
+          lu.op = (int)i;
+          h->units.push_back(lu);
+          continue;
+        }
+      }
+      cur_block = blk;
+      continue;
+    }
+    flush();
+    LaunchUnit lu;
+    lu.op = (int)i;
+    h->units.push_back(lu);
+  }
+  flush();
+  for (size_t u = 0; u < h->units.size(); ++u)
+    if (h->units[u].chain >= 0) {
+      int rc = finish_chain(h, h->chains[h->units[u].chain], (int)u);
+      if (rc) return rc;
+    }
+  return DAD_OK;
+}
+
+int enqueue_chain(dad_handle *h, ChainUnit &cu, int B, cudaStream_t st, int flag_epoch = 1) {
+  ChainParams &p = cu.args.p;
+  p.B = B;
+  p.n_mst = cdiv(B, cu.S_t);
+  p.flag_epoch = flag_epoch;
+  const int entries = cdiv(p.n_mst, 2) * p.n_tiles_n * p.n_convs;
+  // persistent, and never more clusters than can be co-resident: a cluster spins on tiles that other clusters of
+  // this launch produce
+  const int n_cl = std::min(entries, cu.max_clusters);
+  cudaError_t e = chain_ops(cu.GW)->launch(cu.MH, cu.NS, 2 * n_cl, cu.smem, st, cu.args);
+  if (e != cudaSuccess) DAD_FAIL(h, DAD_ERR_CUDA, "conv_chain launch failed (%s ...): %s", h->ops[cu.ops[0]].wname.c_str(), cudaGetErrorString(e));
+  h->counting += 1;
+  return DAD_OK;
 }
 
 template <int BN, int GW>
@@ -710,12 +951,10 @@ static bool step_fused_fits(const dad_handle *h) {
          h->D % 4 == 0;
 }
 
+bool use_small(const dad_handle *h, const ConvOp &op, int B);
+
 int enqueue_tc(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
-  // latency kernels: every sample's CTAs fetch the layer's weights again, so past a re-read budget (256 MB per
-  // layer and launch: never reached by PointMaze below 24 samples, 6 samples of HalfCheetah's largest layer) the throughput kernels win
-  if (op.small && B <= h->small_max_b && !h->rows_t &&
-      (size_t)B * op.Cout_pad * op.g.taps * op.Cin_store * 2 <= ((size_t)256 << 20))
-    return enqueue_small(h, op, B, st);
+  if (use_small(h, op, B)) return enqueue_small(h, op, B, st);
   if (op.t3 && !h->rows_t) return enqueue_t3(h, op, B, st);      // conv_t3 assumes one timestep for the whole batch
   ConvTcParams p = op.tcp;
   p.B = B;
@@ -780,22 +1019,57 @@ bool forks_with_next(const dad_handle *h, size_t i) {
   return false;
 }
 
+// Whether a chain runs as one conv_chain launch for this batch: not when its convs take the latency kernels
+// (small batches) or carry per-row timesteps (stand-alone forward; the generic kernel indexes the tables per row).
+bool use_small(const dad_handle *h, const ConvOp &op, int B) {
+  // latency kernels: every sample's CTAs fetch the layer's weights again, so past a re-read budget (256 MB per
+  // layer and launch: never reached by PointMaze below 24 samples, 6 samples of HalfCheetah's largest layer) the throughput kernels win
+  return op.small && B <= h->small_max_b && !h->rows_t &&
+         (size_t)B * op.Cout_pad * op.g.taps * op.Cin_store * 2 <= ((size_t)256 << 20);
+}
+
+bool use_chain(const dad_handle *h, const ChainUnit &cu, int B) {
+  if (h->rows_t) return false;
+  for (int oi : cu.ops)
+    if (use_small(h, h->ops[oi], B)) return false;
+  return true;
+}
+
 int enqueue_unet(dad_handle *h, int B, cudaStream_t st, bool advance = false, cudaStream_t side = nullptr) {
   const dad_config &c = h->cfg;
   const size_t rows = (size_t)B * c.horizon;
+  const int n_flags = h->d_flags ? (int)h->ops.size() * h->tiles_cap : 0;
   if (h->bf16) {
     const size_t n = rows * (h->Cpad_in / 8);
     launch_k(stage_x_kernel, dim3(cdiv(n, 256)), dim3(256), 0, st, 1, h->d_ls, (float *)nullptr,
-             reinterpret_cast<__nv_bfloat16 *>(act_ptr(h, 0)), rows, c.transition_dim, h->Cpad_in, advance ? 1 : 0);
+             reinterpret_cast<__nv_bfloat16 *>(act_ptr(h, 0)), rows, c.transition_dim, h->Cpad_in, advance ? 1 : 0,
+             h->d_flags, n_flags);
   } else {
     const size_t n = rows * c.transition_dim;
     launch_k(stage_x_kernel, dim3(cdiv(n, 256)), dim3(256), 0, st, 1, h->d_ls, reinterpret_cast<float *>(act_ptr(h, 0)),
-             (__nv_bfloat16 *)nullptr, rows, c.transition_dim, 0, advance ? 1 : 0);
+             (__nv_bfloat16 *)nullptr, rows, c.transition_dim, 0, advance ? 1 : 0, (unsigned *)nullptr, 0);
   }
   h->counting += 1;
-  for (size_t i = 0; i < h->ops.size(); ++i) {
+  // ops in execution order; a chain unit contributes ONE launch when it runs fused
+  std::vector<int> seq;
+  for (const LaunchUnit &lu : h->units) {
+    if (lu.chain >= 0 && h->bf16 && use_chain(h, h->chains[lu.chain], B)) {
+      seq.push_back(-1 - lu.chain);
+    } else if (lu.chain >= 0) {
+      for (int oi : h->chains[lu.chain].ops) seq.push_back(oi);
+    } else {
+      seq.push_back(lu.op);
+    }
+  }
+  for (size_t k = 0; k < seq.size(); ++k) {
+    if (seq[k] < 0) {
+      int rc = enqueue_chain(h, h->chains[-1 - seq[k]], B, st);
+      if (rc) return rc;
+      continue;
+    }
+    const size_t i = (size_t)seq[k];
     const ConvOp &op = h->ops[i];
-    if (side && forks_with_next(h, i)) {
+    if (side && k + 1 < seq.size() && seq[k + 1] == (int)i + 1 && forks_with_next(h, i)) {
       CK(h, cudaEventRecord(h->ev_fork, st));
       CK(h, cudaStreamWaitEvent(side, h->ev_fork, 0));
       int rc = enqueue_tc(h, op, B, st);
@@ -803,7 +1077,7 @@ int enqueue_unet(dad_handle *h, int B, cudaStream_t st, bool advance = false, cu
       if (rc) return rc;
       CK(h, cudaEventRecord(h->ev_join, side));
       CK(h, cudaStreamWaitEvent(st, h->ev_join, 0));
-      ++i;
+      ++k;
       continue;
     }
     int rc = h->bf16 ? enqueue_tc(h, op, B, st) : enqueue_f32(h, op, B, st);
@@ -945,7 +1219,7 @@ int get_graph(dad_handle *h, int B, bool project, GraphEntry **out) {
   h->counting = 0;
   CK(h, cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
   // captured step: [stage x, step index -= 1] -> U-Net -> fused step kernel; the loop starts one index high
-  const bool fork = !(getenv("DAD_FORK") && atoi(getenv("DAD_FORK")) == 0);
+  const bool fork = tuning_env("DAD_FORK", 1) != 0;
   int rc = enqueue_unet(h, B, h->cap_stream, true, fork ? h->side_stream : nullptr);
   if (!rc) rc = enqueue_step(h, h->d_eps, B, project, false, h->cap_stream);
   cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
@@ -1125,7 +1399,20 @@ int dad_create(const dad_config *cfg, dad_handle **out) {
       }
       setup_small_op(h, op);
     }
-  if (getenv("DAD_SMALL_MAX_B")) h->small_max_b = atoi(getenv("DAD_SMALL_MAX_B"));
+  h->small_max_b = tuning_env("DAD_SMALL_MAX_B", h->small_max_b);
+  if (h->bf16) {
+    // tile-completion counters of the conv chains: one row per conv, one word per sample tile (>= 8 samples each)
+    h->tiles_cap = cdiv(c.max_batch, 8);
+    const size_t words = h->ops.size() * (size_t)h->tiles_cap;
+    if ((rc = dev_alloc(h, &h->d_flags, words))) return fail(rc);
+    fill_now(h->d_flags, 0, words * sizeof(unsigned), h->own_stream);
+    if ((rc = dev_alloc(h, &h->d_err, 1))) return fail(rc);
+    fill_now(h->d_err, 0, sizeof(unsigned), h->own_stream);
+    h->fusion = tuning_env("DAD_FUSION", h->fusion);
+  } else {
+    h->fusion = 0;
+  }
+  if ((rc = build_units(h))) return fail(rc);
   if (cudaDeviceSynchronize() != cudaSuccess) { h->err = "device error during create"; return fail(DAD_ERR_CUDA); }
   *out = h;
   return DAD_OK;
@@ -1149,6 +1436,7 @@ int dad_load_weights(dad_handle *h, const dad_tensor *tensors, int32_t n) {
   if (!h || !tensors) return DAD_ERR_INVALID;
   const dad_config &c = h->cfg;
   CK(h, cudaSetDevice(c.device));
+  DAD_QUIESCE(h);
   NamedTensors nt;
   size_t max_numel = 0;
   for (int i = 0; i < n; ++i) {
@@ -1156,18 +1444,18 @@ int dad_load_weights(dad_handle *h, const dad_tensor *tensors, int32_t n) {
     nt.map[tensors[i].name] = &tensors[i];
     max_numel = std::max<size_t>(max_numel, (size_t)tensors[i].numel);
   }
+  DevTemps tmp;                 // freed on every return path
   float *stage = nullptr;
-  CK(h, cudaMalloc(&stage, std::max<size_t>(max_numel, 16) * sizeof(float)));
+  CK(h, tmp.alloc(&stage, max_numel));
   int rc = DAD_OK;
-  auto done = [&](int code) { cudaFree(stage); return code; };
   cudaStream_t st = h->own_stream;
   // ---- convolutions
   for (ConvOp &op : h->ops) {
     const dad_tensor *w = nt.get(op.wname), *b = nt.get(op.bname);
-    if ((rc = check_dims(h, w, op.wname, (long long)op.g.Cout * op.Cin_real * op.ksize))) return done(rc);
-    if ((rc = check_dims(h, b, op.bname, op.g.Cout))) return done(rc);
+    if ((rc = check_dims(h, w, op.wname, (long long)op.g.Cout * op.Cin_real * op.ksize))) return rc;
+    if ((rc = check_dims(h, b, op.bname, op.g.Cout))) return rc;
     const float *wd = nullptr;
-    if ((rc = device_view(h, w, stage, &wd))) return done(rc);
+    if ((rc = device_view(h, w, stage, &wd))) return rc;
     if (h->bf16) {
       const size_t total = (size_t)op.Cout_pad * op.g.taps * op.Cin_store;
       pack_w_bf16_kernel<<<cdiv(total, 256), 256, 0, st>>>(wd, op.w_b16, op.g.Cout, op.Cin_real, op.Cout_pad,
@@ -1181,8 +1469,8 @@ int dad_load_weights(dad_handle *h, const dad_tensor *tensors, int32_t n) {
     CK(h, copy_now(op.bias, b->data, sizeof(float) * op.g.Cout, h->own_stream));
     if (!op.gname.empty()) {
       const dad_tensor *gw = nt.get(op.gname + ".weight"), *gb = nt.get(op.gname + ".bias");
-      if ((rc = check_dims(h, gw, op.gname + ".weight", op.g.Cout))) return done(rc);
-      if ((rc = check_dims(h, gb, op.gname + ".bias", op.g.Cout))) return done(rc);
+      if ((rc = check_dims(h, gw, op.gname + ".weight", op.g.Cout))) return rc;
+      if ((rc = check_dims(h, gb, op.gname + ".bias", op.g.Cout))) return rc;
       CK(h, copy_now(op.gamma, gw->data, sizeof(float) * op.g.Cout, h->own_stream));
       CK(h, copy_now(op.beta, gb->data, sizeof(float) * op.g.Cout, h->own_stream));
     }
@@ -1190,50 +1478,46 @@ int dad_load_weights(dad_handle *h, const dad_tensor *tensors, int32_t n) {
   // ---- time tables: every step index, once (K6)
   const int S = c.n_timesteps, dim = c.dim, td = h->time_dim;
   if (dim / 2 < 2) DAD_FAIL(h, DAD_ERR_INVALID, "dim too small for the sinusoidal embedding");
-  float *emb = nullptr, *h1 = nullptr, *temb = nullptr;
-  CK(h, cudaMalloc(&emb, sizeof(float) * S * dim));
-  CK(h, cudaMalloc(&h1, sizeof(float) * S * td * 4));
-  CK(h, cudaMalloc(&temb, sizeof(float) * S * td));
-  auto done2 = [&](int code) { cudaFree(emb); cudaFree(h1); cudaFree(temb); return done(code); };
+  float *emb = nullptr, *h1 = nullptr, *temb = nullptr, *bd = nullptr;
+  int max_c = td * 4;
+  for (const TimeBlock &tb : h->tblocks) max_c = std::max(max_c, tb.C);
+  CK(h, tmp.alloc(&emb, (size_t)S * dim));
+  CK(h, tmp.alloc(&h1, (size_t)S * td * 4));
+  CK(h, tmp.alloc(&temb, (size_t)S * td));
+  CK(h, tmp.alloc(&bd, (size_t)max_c));
   {
     const dad_tensor *w1 = nt.get("time_mlp.1.weight"), *b1 = nt.get("time_mlp.1.bias");
     const dad_tensor *w3 = nt.get("time_mlp.3.weight"), *b3 = nt.get("time_mlp.3.bias");
-    if ((rc = check_dims(h, w1, "time_mlp.1.weight", (long long)td * 4 * dim))) return done2(rc);
-    if ((rc = check_dims(h, b1, "time_mlp.1.bias", td * 4))) return done2(rc);
-    if ((rc = check_dims(h, w3, "time_mlp.3.weight", (long long)td * td * 4))) return done2(rc);
-    if ((rc = check_dims(h, b3, "time_mlp.3.bias", td))) return done2(rc);
-    float *bd = nullptr;
-    CK(h, cudaMalloc(&bd, sizeof(float) * td * 4));
+    if ((rc = check_dims(h, w1, "time_mlp.1.weight", (long long)td * 4 * dim))) return rc;
+    if ((rc = check_dims(h, b1, "time_mlp.1.bias", td * 4))) return rc;
+    if ((rc = check_dims(h, w3, "time_mlp.3.weight", (long long)td * td * 4))) return rc;
+    if ((rc = check_dims(h, b3, "time_mlp.3.bias", td))) return rc;
     sinusoid_table_kernel<<<cdiv((long long)S * (dim / 2), 256), 256, 0, st>>>(emb, S, dim);
     const float *wd = nullptr;
-    if ((rc = device_view(h, w1, stage, &wd))) { cudaFree(bd); return done2(rc); }
-    copy_now(bd, b1->data, sizeof(float) * td * 4, h->own_stream);
+    if ((rc = device_view(h, w1, stage, &wd))) return rc;
+    CK(h, copy_now(bd, b1->data, sizeof(float) * td * 4, h->own_stream));
     linear_rows_kernel<<<cdiv((long long)S * td * 4, 256), 256, 0, st>>>(emb, wd, bd, h1, S, dim, td * 4, 0, 1);
-    cudaStreamSynchronize(st);
-    if ((rc = device_view(h, w3, stage, &wd))) { cudaFree(bd); return done2(rc); }
-    copy_now(bd, b3->data, sizeof(float) * td, h->own_stream);
+    CK(h, cudaStreamSynchronize(st));
+    if ((rc = device_view(h, w3, stage, &wd))) return rc;
+    CK(h, copy_now(bd, b3->data, sizeof(float) * td, h->own_stream));
     linear_rows_kernel<<<cdiv((long long)S * td, 256), 256, 0, st>>>(h1, wd, bd, temb, S, td * 4, td, 0, 0);
-    cudaStreamSynchronize(st);
-    cudaFree(bd);
+    CK(h, cudaStreamSynchronize(st));
   }
   for (TimeBlock &tb : h->tblocks) {
     const dad_tensor *w = nt.get(tb.stem + ".weight"), *b = nt.get(tb.stem + ".bias");
-    if ((rc = check_dims(h, w, tb.stem + ".weight", (long long)tb.C * td))) return done2(rc);
-    if ((rc = check_dims(h, b, tb.stem + ".bias", tb.C))) return done2(rc);
+    if ((rc = check_dims(h, w, tb.stem + ".weight", (long long)tb.C * td))) return rc;
+    if ((rc = check_dims(h, b, tb.stem + ".bias", tb.C))) return rc;
     const float *wd = nullptr;
-    if ((rc = device_view(h, w, stage, &wd))) return done2(rc);
-    float *bd = nullptr;
-    CK(h, cudaMalloc(&bd, sizeof(float) * tb.C));
-    copy_now(bd, b->data, sizeof(float) * tb.C, h->own_stream);
+    if ((rc = device_view(h, w, stage, &wd))) return rc;
+    CK(h, copy_now(bd, b->data, sizeof(float) * tb.C, h->own_stream));
     linear_rows_kernel<<<cdiv((long long)S * tb.C, 256), 256, 0, st>>>(temb, wd, bd, tb.tab, S, td, tb.C, 1, 0);
-    cudaStreamSynchronize(st);
-    cudaFree(bd);
+    CK(h, cudaStreamSynchronize(st));
   }
   cudaError_t e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaGetLastError();
-  if (e != cudaSuccess) { h->err = std::string("weight packing failed: ") + cudaGetErrorString(e); return done2(DAD_ERR_CUDA); }
+  if (e != cudaSuccess) { h->err = std::string("weight packing failed: ") + cudaGetErrorString(e); return DAD_ERR_CUDA; }
   h->have_weights = true;
-  return done2(DAD_OK);
+  return DAD_OK;
 }
 
 int dad_set_schedule(dad_handle *h, const float *sr, const float *srm1, const float *c1, const float *c2,
@@ -1241,6 +1525,7 @@ int dad_set_schedule(dad_handle *h, const float *sr, const float *srm1, const fl
   if (!h || !sr || !srm1 || !c1 || !c2 || !lv) return DAD_ERR_INVALID;
   if (n != h->cfg.n_timesteps) DAD_FAIL(h, DAD_ERR_INVALID, "schedule length %d != n_timesteps %d", n, h->cfg.n_timesteps);
   CK(h, cudaSetDevice(h->cfg.device));
+  DAD_QUIESCE(h);
   const float *src[5] = {sr, srm1, c1, c2, lv};
   for (int i = 0; i < 5; ++i) CK(h, copy_now(h->d_sched[i], src[i], sizeof(float) * n, h->own_stream));
   h->have_sched = true;
@@ -1250,6 +1535,7 @@ int dad_set_schedule(dad_handle *h, const float *sr, const float *srm1, const fl
 int dad_set_projector(dad_handle *h, const float *Nmat, const float *q, const float *alpha, int32_t D, int32_t n) {
   if (!h) return DAD_ERR_INVALID;
   CK(h, cudaSetDevice(h->cfg.device));
+  DAD_QUIESCE(h);
   if (!Nmat) { h->projD = 0; return DAD_OK; }
   if (!q || !alpha) return DAD_ERR_INVALID;
   if (D != h->D) DAD_FAIL(h, DAD_ERR_INVALID, "projector dimension %d != horizon*transition_dim %d", D, h->D);
@@ -1270,7 +1556,7 @@ int dad_set_projector(dad_handle *h, const float *Nmat, const float *q, const fl
   CK(h, cudaStreamSynchronize(h->own_stream));
   h->projD = D;
   h->proj_tc = false;
-  if (h->bf16 && !(getenv("DAD_PROJ_TC") && atoi(getenv("DAD_PROJ_TC")) == 0)) {
+  if (h->bf16 && tuning_env("DAD_PROJ_TC", 1) != 0) {
     const int Kp = (D + 63) / 64 * 64, Np = (D + 127) / 128 * 128;
     if (!h->d_projW) {
       int rc;
@@ -1305,6 +1591,7 @@ int dad_set_conditions(dad_handle *h, const int32_t *h_idx, const float *vals, i
                        int32_t B) {
   if (!h) return DAD_ERR_INVALID;
   CK(h, cudaSetDevice(h->cfg.device));
+  DAD_QUIESCE(h);
   if (n_cond <= 0) { h->n_cond = 0; return DAD_OK; }
   if (!h_idx || !vals) return DAD_ERR_INVALID;
   if (n_cond > kMaxCond) DAD_FAIL(h, DAD_ERR_INVALID, "at most %d conditions are supported (got %d)", kMaxCond, n_cond);
@@ -1317,7 +1604,7 @@ int dad_set_conditions(dad_handle *h, const int32_t *h_idx, const float *vals, i
   const size_t need = (size_t)n_cond * (per_batch ? B : 1) * h->cfg.transition_dim;
   if (need > h->cond_cap) {
     int rc;
-    if ((rc = dev_alloc(h, &h->d_cond, need))) return rc;
+    if ((rc = dev_regrow(h, &h->d_cond, need))) return rc;
     h->cond_cap = need;
     drop_graphs(h);
   }
@@ -1341,6 +1628,7 @@ int dad_unet_forward(dad_handle *h, const float *x, const int64_t *t, int32_t st
     ls.n_steps = step + 1;
     ls.x = const_cast<float *>(x) + (size_t)c0 * h->D;
     ls.t_rows = t ? reinterpret_cast<const long long *>(t) + c0 : nullptr;
+    ls.n_table = h->cfg.n_timesteps;
     int rc = set_loop_state(h, ls, st);
     if (rc) return rc;
     h->counting = 0;
@@ -1566,7 +1854,8 @@ int dad_sample_host(dad_handle *h, float *x_host, const float *noise_seq_host, u
   const size_t n = (size_t)B * h->D;
   if (n > h->hostx_cap) {
     int rc;
-    if ((rc = dev_alloc(h, &h->d_hostx, n))) return rc;
+    CK(h, cudaStreamSynchronize(h->own_stream));
+    if ((rc = dev_regrow(h, &h->d_hostx, n))) return rc;
     h->hostx_cap = n;
   }
   const float *d_noise = nullptr;
@@ -1574,7 +1863,8 @@ int dad_sample_host(dad_handle *h, float *x_host, const float *noise_seq_host, u
     const size_t nn = n * (size_t)n_steps;
     if (nn > h->hostnoise_cap) {
       int rc;
-      if ((rc = dev_alloc(h, &h->d_hostnoise, nn))) return rc;
+      CK(h, cudaStreamSynchronize(h->own_stream));
+      if ((rc = dev_regrow(h, &h->d_hostnoise, nn))) return rc;
       h->hostnoise_cap = nn;
     }
     CK(h, cudaMemcpyAsync(h->d_hostnoise, noise_seq_host, sizeof(float) * nn, cudaMemcpyHostToDevice, h->own_stream));
@@ -1593,7 +1883,10 @@ int dad_get_info(const dad_handle *h, dad_info *out) {
   if (!h || !out) return DAD_ERR_INVALID;
   out->conv_flops_per_sample = h->conv_flops;
   long long per_step = 1;  // stage_x
-  for (const ConvOp &op : h->ops) per_step += (h->bf16 || op.gname.empty()) ? 1 : 2;
+  for (const LaunchUnit &lu : h->units) {
+    if (lu.chain >= 0) per_step += 1;
+    else per_step += (h->bf16 || h->ops[lu.op].gname.empty()) ? 1 : 2;
+  }
   per_step += 1;           // fused step kernel (the projector GEMM adds one for large D)
   out->launches_per_step = per_step;
   out->workspace_bytes = (int64_t)(h->act_bytes_per_sample * (size_t)h->cfg.max_batch);
@@ -1671,7 +1964,11 @@ int dad_layer_info(const dad_handle *h, int32_t index, dad_layer_desc *out) {
   out->tile_n = op.t3 ? 128 * op.t3_NS : op.BN;
   out->group_width = op.GW;
   if (!h->bf16) snprintf(out->kernel, sizeof(out->kernel), "conv_f32_kernel%s", op.gname.empty() ? "" : "+gn_mish_f32_kernel");
-  else if (op.t3) {
+  else if (op.chain >= 0) {
+    const ChainUnit &cu = h->chains[h->units[op.chain].chain];
+    snprintf(out->kernel, sizeof(out->kernel), "conv_chain_kernel<GW=%d,MH=%d,N=%d>", cu.GW, cu.MH, 128 * cu.NS);
+    out->tile_n = 128 * cu.NS;
+  } else if (op.t3) {
     static const char *modes[3] = {"single", "mcast", "pair"};
     snprintf(out->kernel, sizeof(out->kernel), "conv_t3_kernel<GW=%d,MH=%d,%s,N=%d>", op.GW, op.t3_MH, modes[op.t3_mode], 128 * op.t3_NS);
   } else snprintf(out->kernel, sizeof(out->kernel), "conv_tc_kernel<%d,%d>", op.BN, op.GW);
@@ -1693,7 +1990,7 @@ int dad_time_layer(dad_handle *h, int32_t index, int32_t B, int32_t iters, float
   if (rc) return rc;
   ConvOp &op = h->ops[index];
   unsigned long long *prof = nullptr;
-  if (h->bf16 && getenv("DAD_TC_PROF")) {
+  if (h->bf16 && tuning_env("DAD_TC_PROF", 0)) {
     CK(h, cudaMalloc(&prof, 4 * sizeof(unsigned long long)));
     CK(h, fill_now(prof, 0, 4 * sizeof(unsigned long long), h->own_stream));
     op.tcp.prof = prof;
@@ -1715,6 +2012,64 @@ int dad_time_layer(dad_handle *h, int32_t index, int32_t B, int32_t iters, float
   return rc;
 }
 
+int dad_set_fusion(dad_handle *h, int32_t level) {
+  if (!h || level < 0 || level > 3) return DAD_ERR_INVALID;
+  if (!h->bf16) return DAD_OK;                 // fp32 mode has no chains
+  if (level == h->fusion) return DAD_OK;
+  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaDeviceSynchronize());
+  drop_graphs(h);
+  h->fusion = level;
+  return build_units(h);
+}
+
+int dad_unit_count(const dad_handle *h) { return h ? (int)h->units.size() : 0; }
+
+int dad_unit_info(const dad_handle *h, int32_t index, dad_unit_desc *out) {
+  if (!h || !out || index < 0 || index >= (int)h->units.size()) return DAD_ERR_INVALID;
+  memset(out, 0, sizeof(*out));
+  const LaunchUnit &lu = h->units[index];
+  std::vector<int> ops;
+  if (lu.chain >= 0) ops = h->chains[lu.chain].ops; else ops.push_back(lu.op);
+  out->first_layer = ops.front();
+  out->n_layers = (int)ops.size();
+  out->is_chain = lu.chain >= 0 ? 1 : 0;
+  const ConvOp &last = h->ops[ops.back()];
+  out->L_out = last.g.L_out;
+  out->C_out = last.g.Cout;
+  for (int oi : ops) out->flops_per_sample += 2LL * h->ops[oi].g.L_out * h->ops[oi].g.taps * h->ops[oi].Cin_real * h->ops[oi].g.Cout;
+  dad_layer_desc d;
+  dad_layer_info(h, ops.front(), &d);
+  snprintf(out->kernel, sizeof(out->kernel), "%s", d.kernel);
+  return DAD_OK;
+}
+
+int dad_time_unit(dad_handle *h, int32_t index, int32_t B, int32_t iters, float *ms, void *stream) {
+  if (!h || !ms || index < 0 || index >= (int)h->units.size() || iters < 1 || B < 1 || B > h->cfg.max_batch) return DAD_ERR_INVALID;
+  if (!h->have_weights) DAD_FAIL(h, DAD_ERR_STATE, "dad_time_unit before dad_load_weights");
+  const LaunchUnit &lu = h->units[index];
+  if (lu.chain < 0) return dad_time_layer(h, lu.op, B, iters, ms, stream);
+  CK(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  LoopState ls{};
+  ls.step = 0;
+  ls.n_steps = 1;
+  ls.x = h->d_xtmp;
+  int rc = set_loop_state(h, ls, st);
+  if (rc) return rc;
+  ChainUnit &cu = h->chains[lu.chain];
+  if (!use_chain(h, cu, B)) DAD_FAIL(h, DAD_ERR_INVALID, "unit %d does not run as a chain at B=%d (latency kernels)", index, B);
+  CK(h, cudaMemsetAsync(h->d_flags, 0, h->ops.size() * (size_t)h->tiles_cap * sizeof(unsigned), st));
+  int epoch = 0;
+  h->counting = 0;
+  rc = time_launches(h, st, iters, ms, [&]() { return enqueue_chain(h, cu, B, st, ++epoch); });
+  h->launches += h->counting;
+  // leave the counters as a U-Net pass expects to find them
+  CK(h, cudaMemsetAsync(h->d_flags, 0, h->ops.size() * (size_t)h->tiles_cap * sizeof(unsigned), st));
+  CK(h, cudaStreamSynchronize(st));
+  return rc;
+}
+
 int dad_time_step_kernel(dad_handle *h, int32_t B, int32_t step, uint32_t flags, int32_t iters, float *ms, void *stream) {
   if (!h || !ms || iters < 1 || B < 1 || B > h->cfg.max_batch) return DAD_ERR_INVALID;
   if (!h->have_sched) DAD_FAIL(h, DAD_ERR_STATE, "dad_time_step_kernel before dad_set_schedule");
@@ -1726,7 +2081,8 @@ int dad_time_step_kernel(dad_handle *h, int32_t B, int32_t step, uint32_t flags,
   const size_t n = (size_t)B * h->D;
   if (n > h->hostx_cap) {
     int rc;
-    if ((rc = dev_alloc(h, &h->d_hostx, n))) return rc;
+    CK(h, cudaDeviceSynchronize());
+    if ((rc = dev_regrow(h, &h->d_hostx, n))) return rc;
     h->hostx_cap = n;
   }
   CK(h, cudaMemsetAsync(h->d_hostx, 0, n * sizeof(float), st));
@@ -1735,7 +2091,8 @@ int dad_time_step_kernel(dad_handle *h, int32_t B, int32_t step, uint32_t flags,
   if (injected) {
     if (n > h->hostnoise_cap) {
       int rc;
-      if ((rc = dev_alloc(h, &h->d_hostnoise, n))) return rc;
+      CK(h, cudaDeviceSynchronize());
+      if ((rc = dev_regrow(h, &h->d_hostnoise, n))) return rc;
       h->hostnoise_cap = n;
     }
     CK(h, cudaMemsetAsync(h->d_hostnoise, 0, n * sizeof(float), st));

@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(128) gn_mish_f32_kernel(const GnF32Params p) {
   const float var = block_sum(q, red) / (float)n;
   const float rstd = 1.0f / sqrtf(var + kGnEps);
   long long t = 0;
-  if (p.ttab) t = p.ls->t_rows ? p.ls->t_rows[b] : (long long)p.ls->step;
+  if (p.ttab) t = p.ls->t_rows ? min(max(p.ls->t_rows[b], 0ll), (long long)p.ls->n_table - 1) : (long long)p.ls->step;
   for (int e = threadIdx.x; e < n; e += blockDim.x) {
     const int l = e / gw, j = e - l * gw;
     const int c = grp * gw + j;

@@ -11,7 +11,7 @@
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
-#include "conv_t3.cuh"   // packed fp32x2 helpers
+#include "f32x2.cuh"
 
 namespace dad {
 
@@ -406,13 +406,17 @@ __global__ void set_loop_state_kernel(LoopState *dst, const LoopState v) { *dst 
 // fp32 copy (fp32 mode) or bf16 with zero-padded channels (bf16 mode; 8 channels = one 16-byte store per thread).
 // With `advance` the kernel also moves the loop to its next step index: it is the FIRST kernel of the captured
 // step, does not read the index itself, and every later kernel of the step sees the new value.
+// It also zeroes the tile-completion counters of the conv chains (conv_chain.cuh): every kernel of the previous pass
+// has completed when this one passes its dependency wait, and every kernel of this pass waits for this one.
 __global__ void __launch_bounds__(256) stage_x_kernel(LoopState *lsp, float *out_f32, __nv_bfloat16 *out_bf16,
-                                                       size_t rows, int T, int Cpad, int advance) {
+                                                       size_t rows, int T, int Cpad, int advance, unsigned *flags,
+                                                       int n_flags) {
   ptx::griddep_launch();
   ptx::griddep_wait();
   const float *x = lsp->x;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (advance && idx == 0) lsp->step -= 1;
+  for (size_t i = idx; i < (size_t)n_flags; i += (size_t)gridDim.x * blockDim.x) flags[i] = 0u;
   if (out_bf16) {
     const int vec = Cpad >> 3;
     if (idx >= rows * (size_t)vec) return;

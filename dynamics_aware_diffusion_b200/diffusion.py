@@ -76,17 +76,23 @@ class GaussianDiffusion(nn.Module):
         if loss_type not in ("l1", "l2"):
             raise ValueError(f"Unknown loss type: {loss_type}")
         self.loss_type = loss_type
+        # the stand-alone model(x, t) call shares the engine (and its time tables) with the sampling loop
+        model._n_timesteps = int(betas.shape[0])
 
     # ---- native plumbing ------------------------------------------------------------------------
+    _SCHEDULE_BUFFERS = ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
+                         "posterior_mean_coef2", "posterior_log_variance_clipped")
+
     def _schedule_version(self):
-        return sum(getattr(self, n)._version for n in
-                   ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
-                    "posterior_mean_coef2", "posterior_log_variance_clipped"))
+        """(address, version) per table + their sums: also sees writes through `.data` (see TemporalUnet._weights_version)."""
+        bufs = [getattr(self, n) for n in self._SCHEDULE_BUFFERS]
+        return (tuple((b.data_ptr(), b._version) for b in bufs), float(torch.stack([b.double().sum() for b in bufs]).sum()))
 
     def engine(self, horizon=None, device=None):
         """Native handle with this process's weights and schedule tables loaded (rebuilt lazily on change)."""
         device = device if device is not None else self.betas.device
         self.model._diffusion_cfg = dict(predict_epsilon=bool(self.predict_epsilon), clip_denoised=bool(self.clip_denoised))
+        self.model._n_timesteps = int(self.betas.shape[0])
         eng, ent = self.model.engine(horizon or self.horizon, device, n_timesteps=self.betas.shape[0])
         tag = (id(self), self._schedule_version())
         if ent.get("schedule_owner") != tag:

@@ -53,6 +53,7 @@ class Engine:
             raise N.DadError(rc, msg.decode() if msg else "dad_create failed")
         self._keep = []          # tensors whose device memory the handle may still read asynchronously
         self.has_projector = False
+        self.projector_tag = None        # who pushed the projector that is loaded now (DynamicsAwarePolicy._push_projector)
 
     def close(self):
         if getattr(self, "handle", None) and self.handle.value:
@@ -80,15 +81,17 @@ class Engine:
             arr[i].name = kb
             arr[i].data = v.data_ptr()
             arr[i].numel = v.numel()
-        if any(v.is_cuda for _, v in items):
-            torch.cuda.synchronize(self.device)
+        torch.cuda.synchronize(self.device)      # sampling still in flight reads the tables this call rewrites
         self._ck(self.lib.dad_load_weights(self.handle, arr, len(items)))
 
     def set_schedule(self, sqrt_recip, sqrt_recipm1, coef1, coef2, log_var):
         ts = [t.detach().to("cpu", torch.float32).contiguous() for t in (sqrt_recip, sqrt_recipm1, coef1, coef2, log_var)]
+        torch.cuda.synchronize(self.device)
         self._ck(self.lib.dad_set_schedule(self.handle, *[_ptr(t) for t in ts], ts[0].numel()))
 
     def set_projector(self, Nmat, q, alpha):
+        torch.cuda.synchronize(self.device)
+        self.projector_tag = None
         if Nmat is None:
             self._ck(self.lib.dad_set_projector(self.handle, None, None, None, 0, 0))
             self.has_projector = False
@@ -228,6 +231,28 @@ class Engine:
         with torch.cuda.device(self.device):
             self._ck(self.lib.dad_time_layer(self.handle, int(index), int(B), int(iters), ctypes.byref(ms), _stream()))
         return ms.value
+
+    def units(self):
+        """Launch units of one U-Net pass at the current fusion level (a conv chain or a single layer)."""
+        out = []
+        for i in range(self.lib.dad_unit_count(self.handle)):
+            d = N.DadUnitDesc()
+            self._ck(self.lib.dad_unit_info(self.handle, i, ctypes.byref(d)))
+            out.append({"index": i, "first_layer": d.first_layer, "n_layers": d.n_layers, "is_chain": bool(d.is_chain),
+                        "L_out": d.L_out, "C_out": d.C_out, "flops_per_sample": d.flops_per_sample,
+                        "kernel": d.kernel.decode()})
+        return out
+
+    def time_unit(self, index, B, iters=20):
+        ms = ctypes.c_float()
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.dad_time_unit(self.handle, int(index), int(B), int(iters), ctypes.byref(ms), _stream()))
+        return ms.value
+
+    def set_fusion(self, level):
+        """0 = per-layer kernels of round 1, 1 = chain kernel per conv, 2 = per ResidualTemporalBlock, 3 = per run of
+        blocks (default)."""
+        self._ck(self.lib.dad_set_fusion(self.handle, int(level)))
 
     def time_step_kernel(self, B, step, flags=0, iters=20):
         ms = ctypes.c_float()

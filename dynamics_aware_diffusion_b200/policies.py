@@ -294,8 +294,8 @@ class DynamicsAwarePolicy(GuidedPolicy):
             if normalizer is not None:
                 val = torch.from_numpy(np.asarray(getattr(normalizer, name))).float().to(self.device)
             setattr(self, name, val)
-        self._fold = None          # (Nmat, q) fp64
-        self._loaded_on = None     # (engine id, alpha signature) the projector was last pushed to
+        self._fold = None          # (Nmat, q) fp64, rebuilt when the matrix or the normaliser changes
+        self._fold_tag, self._fold_serial = None, 0
 
     def _get_projection_alpha(self, t: int) -> float:
         betas = self.diffusion.betas if self.projection_schedule == "noise_schedule" else None
@@ -318,21 +318,38 @@ class DynamicsAwarePolicy(GuidedPolicy):
     def _active(self):
         return self.projection_matrix is not None and self.normalizer is not None
 
+    def _projector_inputs_tag(self):
+        """Identity of everything the folded map (N, q) is made of: the matrix object (and its in-place version) and
+        the normaliser statistics by value.  A new `policy.projection_matrix` or normaliser rebuilds the fold."""
+        P = self.projection_matrix
+        ptag = (id(P), getattr(P, "_version", None), P.data_ptr() if torch.is_tensor(P) else None)
+        stats = tuple(np.asarray(getattr(self.normalizer, n), dtype=np.float64).tobytes()
+                      for n in ("obs_mean", "obs_std", "action_mean", "action_std"))
+        return (ptag, stats, self.state_dim, self.action_dim, self.horizon)
+
     def _push_projector(self, eng):
-        if self._fold is None:
-            if self.observation_dim != self.state_dim:
-                raise RuntimeError("projection needs observation_dim == state_dim (the reference's apply_projection "
-                                   "fails otherwise, SURVEY.md F4)")
-            self._fold = fold_projection(self.projection_matrix.detach().cpu().numpy(), self.normalizer.obs_mean,
-                                         self.normalizer.obs_std, self.normalizer.action_mean,
-                                         self.normalizer.action_std, self.state_dim, self.action_dim, self.horizon)
+        if self.observation_dim != self.state_dim:
+            raise RuntimeError("projection needs observation_dim == state_dim (the reference's apply_projection "
+                               "fails otherwise, SURVEY.md F4)")
+        ftag = self._projector_inputs_tag()
+        if self._fold is None or self._fold_tag != ftag:
+            P = self.projection_matrix
+            P = P.detach().cpu().numpy() if torch.is_tensor(P) else np.asarray(P)
+            self._fold = fold_projection(P, self.normalizer.obs_mean, self.normalizer.obs_std,
+                                         self.normalizer.action_mean, self.normalizer.action_std, self.state_dim,
+                                         self.action_dim, self.horizon)
+            self._fold_tag = ftag
+            self._fold_serial += 1
         n_table = self.diffusion.betas.shape[0]
         betas = self.diffusion.betas if self.projection_schedule == "noise_schedule" else None
         alphas = projection_alphas(n_table, self.n_timesteps, self.projection_schedule, self.projection_strength, betas)
-        sig = (id(eng), self.projection_schedule, float(self.projection_strength), int(self.n_timesteps), n_table)
-        if self._loaded_on != sig:
+        # the handle is shared by every policy built on this diffusion model: the "currently loaded" tag lives on the
+        # ENGINE (like the schedule's owner tag), so policy A re-pushes after policy B used the same handle
+        sig = (id(self), self._fold_serial, self.projection_schedule, float(self.projection_strength),
+               int(self.n_timesteps), n_table, alphas.tobytes())
+        if getattr(eng, "projector_tag", None) != sig:
             eng.set_projector(self._fold[0], self._fold[1], alphas)
-            self._loaded_on = sig
+            eng.projector_tag = sig
 
     def _loop_flags(self, eng):
         if not (self._active() and self.project_in_loop):

@@ -70,7 +70,7 @@ class TemporalUnet(nn.Module):
         self.transition_dim = transition_dim
         self.dim, self.dim_mults, self.kernel_size = dim, tuple(dim_mults), kernel_size
         self.time_dim = time_dim or dim
-        self.precision = os.environ.get("DAD_PRECISION", precision)
+        self.precision = precision
         self.max_batch = max_batch or _DEFAULT_MAX_BATCH
         self.latency_max_batch = latency_max_batch
         td = self.time_dim
@@ -97,12 +97,34 @@ class TemporalUnet(nn.Module):
                 Upsample1d(ci)]))
         self.final_conv = nn.Sequential(Conv1dBlock(dim, dim, kernel_size=kernel_size), nn.Conv1d(dim, transition_dim, 1))
         self._engines = {}
-        self._n_timesteps = 1000      # table length for a stand-alone forward; GaussianDiffusion overrides
+        self._n_timesteps = 1000      # time-table length for a stand-alone forward; GaussianDiffusion sets it to its schedule length
+        self._force_reload, self._reload_count = False, 0
         self._diffusion_cfg = dict(predict_epsilon=True, clip_denoised=True)
 
     # ---- native engine management ---------------------------------------------------------------
     def _weights_version(self):
-        return sum(p._version for p in self.parameters())
+        """Change tag of the parameters: (storage address, autograd version) of every tensor catches optimizer steps,
+        `load_state_dict` and `p.data = new`; a device checksum catches in-place writes THROUGH `.data`
+        (`p.data.copy_()`, `p.data.mul_()`: EMA.apply_shadow / Trainer.update_ema / NCCL broadcasts), which bump
+        neither.  One fused norm kernel + one scalar read per call."""
+        params = [p for p in self.parameters()]
+        tag = tuple((p.data_ptr(), p._version) for p in params)
+        if self._force_reload:
+            self._force_reload = False
+            self._reload_count += 1
+        dev = [p.detach() for p in params if p.is_cuda]
+        check = 0.0
+        if dev:
+            norms = torch.stack(torch._foreach_norm(dev, 1)).double()
+            check = float((norms * torch.arange(1, norms.numel() + 1, device=norms.device, dtype=torch.float64)).sum())
+        return (tag, check, self._reload_count)
+
+    def invalidate(self):
+        """Force the native handles to re-pack the weights on their next use (call after writing parameters in a way
+        PyTorch does not track)."""
+        self._force_reload = True
+
+    refresh_weights = invalidate
 
     def engine(self, horizon, device, n_timesteps=None, min_batch=1):
         """The native handle for (horizon, device); rebuilt when shapes change, re-packed when weights change."""
@@ -132,5 +154,14 @@ class TemporalUnet(nn.Module):
         """x: (B, H, T) fp32 CUDA, time: (B,) integer timesteps -> (B, H, T)   (temporal_unet.py:199-241)."""
         if x.dim() != 3 or x.shape[2] != self.transition_dim:
             raise ValueError("x must be (batch, horizon, %d)" % self.transition_dim)
+        time = time.reshape(-1)
+        if time.is_floating_point():
+            if not bool((time == time.round()).all()):
+                raise ValueError("time must hold integer timesteps: the time-embedding tables are indexed by step")
+            time = time.long()
+        lo, hi = (int(v) for v in torch.aminmax(time))
+        if lo < 0 or hi >= self._n_timesteps:
+            raise IndexError("timesteps must lie in [0, %d) (got %d..%d): the tables are built for the diffusion's "
+                             "schedule length" % (self._n_timesteps, lo, hi))
         eng, _ = self.engine(x.shape[1], x.device)
-        return eng.unet_forward(x.contiguous().float(), t=time.reshape(-1))
+        return eng.unet_forward(x.contiguous().float(), t=time)

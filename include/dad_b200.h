@@ -171,6 +171,12 @@ int64_t dad_launch_count(const dad_handle *h);
  * latency kernels; the default is 24, about where the throughput kernels take over on a B200 (or the
  * DAD_SMALL_MAX_B environment variable).  bf16 mode only. */
 int dad_set_latency_batch(dad_handle *h, int32_t max_b);
+/* How the stride-1 convolutions of the U-Net (temporal_unet.py:106-122, 214-237) are grouped into launches, bf16
+ * mode: 3 (default) = one persistent conv_chain launch per run of ResidualTemporalBlocks of one level (their convs
+ * synchronise through per-sample-tile counters instead of kernel boundaries), 2 = one launch per block, 1 = one
+ * launch per convolution with the same kernel, 0 = the per-layer kernels of round 1 (conv_t3).  Results are
+ * bit-identical at levels 1-3.  Drops the captured steps (dad_graph_epoch changes). */
+int dad_set_fusion(dad_handle *h, int32_t level);
 
 /* ---- guided sampling inside a caller-captured CUDA graph -------------------------------------------
  * ValueGuidedPolicy (policies.py:243-271) differentiates a user value model at x_t every step
@@ -224,6 +230,20 @@ int dad_layer_info(const dad_handle *h, int32_t index, dad_layer_desc *out);
  * untimed launch); *ms_per_launch receives the average.  Operates on the handle's own workspaces (their
  * contents are whatever the last forward left there).  Synchronises. */
 int dad_time_layer(dad_handle *h, int32_t index, int32_t B, int32_t iters, float *ms_per_launch, void *stream);
+/* Launch units of one U-Net pass at the current fusion level: a conv chain (layers [first_layer, first_layer +
+ * n_layers) in ONE launch) or a single layer. */
+typedef struct {
+  int32_t first_layer, n_layers;
+  int32_t is_chain;
+  int32_t L_out, C_out;
+  int64_t flops_per_sample;      /* sum over the unit's layers */
+  char kernel[64];
+} dad_unit_desc;
+int dad_unit_count(const dad_handle *h);
+int dad_unit_info(const dad_handle *h, int32_t index, dad_unit_desc *out);
+/* dad_time_layer for a whole launch unit (the chain's counters are reset before the loop and every launch waits
+ * for its own epoch, so the in-chain dependencies are exercised exactly as in a U-Net pass). */
+int dad_time_unit(dad_handle *h, int32_t index, int32_t B, int32_t iters, float *ms_per_launch, void *stream);
 /* Same for the fused step kernel(s) (K7 [+K8]) at step index `step` on scratch trajectories; Philox noise, or a
  * noise buffer when flags has bit 0x100 set (the parity-mode data path: 16 instead of 12 bytes per element). */
 int dad_time_step_kernel(dad_handle *h, int32_t B, int32_t step, uint32_t flags, int32_t iters,

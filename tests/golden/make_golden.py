@@ -183,8 +183,65 @@ def make_case(name, ref):
         name, len(ref_keys), float(np.abs(out["trace_dyn"][-1]).mean()), out["residual_dyn"][0], out["residual_dyn"][-1]))
 
 
+def make_full_case(name, ref):
+    """Light golden file of a full-width architecture (helpers.FULL_CASES): raw U-Net outputs (uniform and per-row
+    timesteps) and the dynamics-aware composition traced per step, with its residuals.  P itself (up to 2183^2) is
+    not stored: tests rebuild it from the stored (A, B) and check it against P_diag / P_row0 / P_fro."""
+    c = helpers.FULL_CASES[name]
+    T, S, B, H = helpers.case_T(c), c["S"], c["B"], c["H"]
+    sd, _ = helpers.make_state_dict(c)
+    torch.manual_seed(0)
+    net = ref.TemporalUnet(T, dim=c["dim"], dim_mults=c["mults"])
+    dif = ref.GaussianDiffusion(net, horizon=H, observation_dim=c["n"], action_dim=c["m"], n_timesteps=S,
+                                beta_schedule=c["beta"])
+    ref_keys = list(dif.state_dict().keys())
+    assert ref_keys == list(sd.keys()), "state_dict key order/layout differs from the reference"
+    dif.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    dif.eval()
+    out = {"case": np.array(helpers.case_json(c)), "n_keys": np.array(len(ref_keys)),
+           "n_params": np.array(sum(p.numel() for p in net.parameters()))}
+    x_init, z, start, goal = helpers.noise_inputs(c)
+    out.update(x_init=x_init, noise=z, start=start, goal=goal)
+    nz = helpers.normalizer(c)
+    cond0 = {0: torch.from_numpy(start)[None]}
+    with torch.no_grad():
+        xt = torch.from_numpy(x_init)
+        steps = sorted({0, S - 1})
+        out["unet_steps"] = np.array(steps, dtype=np.int64)
+        out["unet_eps"] = np.stack([net(xt, torch.full((B,), i, dtype=torch.long)).numpy() for i in steps])
+        t_rows = (np.arange(B) * 2 + 1) % S
+        out["unet_t_rows"] = t_rows.astype(np.int64)
+        out["unet_eps_rows"] = net(xt, torch.from_numpy(t_rows).long()).numpy()
+        dyn = helpers.dynamics(c)
+        with contextlib.redirect_stdout(io.StringIO()):
+            A, Bm = ref.fit_linear_dynamics(dyn[2], dyn[3], dyn[4])
+            P = ref.ProjectionMatrixBuilder(A, Bm, c["n"], c["m"]).get_projection_matrix(H)
+            dpol = ref.DynamicsAwarePolicy(dif, projection_matrix=P, normalizer=nz, state_dim=c["n"],
+                                           observation_dim=c["n"], action_dim=c["m"], horizon=H,
+                                           projection_schedule=c["proj_schedule"], projection_strength=c["strength"])
+        out["A"], out["Bm"] = np.asarray(A, dtype=np.float64), np.asarray(Bm, dtype=np.float64)
+        out["P_diag"] = torch.diagonal(P).numpy().copy()
+        out["P_row0"] = P[0].numpy().copy()
+        out["P_fro"] = np.array(float(torch.linalg.norm(P.double())))
+        out["alphas"] = np.array([dpol._get_projection_alpha(i) for i in range(S)], dtype=np.float64)
+        trace, res = [], []
+        with injected_noise(x_init, z):
+            x = dpol.apply_conditions(torch.randn((B, H, T)), cond0)
+            for i in reversed(range(S)):
+                x = dpol.p_sample_with_guidance(x, torch.full((B,), i, dtype=torch.long), None)
+                x = dpol.apply_projection(x, i)
+                x = dpol.apply_conditions(x, cond0)
+                trace.append(x.numpy().copy())
+                res.append(residual(concat_physical(dpol, x), P))
+        out["trace_dyn"] = np.stack(trace)
+        out["residual_dyn"] = np.array(res, dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("%-12s params=%d  |eps|=%.4f  residual %.3e -> %.3e" % (
+        name, int(out["n_params"]), float(np.abs(out["unet_eps"]).mean()), out["residual_dyn"][0], out["residual_dyn"][-1]))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     ref = ref_shim.load()
-    for name in (sys.argv[1:] or helpers.CASES):
-        make_case(name, ref)
+    for name in (sys.argv[1:] or list(helpers.CASES) + list(helpers.FULL_CASES)):
+        (make_full_case if name in helpers.FULL_CASES else make_case)(name, ref)

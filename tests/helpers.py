@@ -39,6 +39,22 @@ CASES = {
 }
 
 
+# The REAL HalfCheetah / Door architectures (README.md:177-179, 194-196): dim 256, GroupNorm
+# widths 32 / 128 / 256 and C_out up to 2048 -- the kernel instantiations the reduced-width cases above never reach.
+# Kept out of CASES (235-252 M parameters: the full parametrised suite would take minutes per case); they have their
+# own light golden files (raw U-Net outputs + the dynamics-aware trace) and dedicated tests.
+FULL_CASES = {
+    "cheetah_full": dict(n=17, m=6, dim=256, mults=(1, 4, 8), H=32, S=3, B=3, beta="cosine", dyn="data_driven",
+                         proj_schedule="noise_schedule", strength=1.0, wseed=203),
+    "door_full": dict(n=39, m=28, dim=256, mults=(1, 2, 4, 8), H=32, S=3, B=2, beta="cosine", dyn="data_driven",
+                      proj_schedule="noise_schedule", strength=1.0, wseed=204),
+}
+
+
+def any_case(name):
+    return CASES[name] if name in CASES else FULL_CASES[name]
+
+
 def case_T(c):
     return c["n"] + c["m"]
 

@@ -24,6 +24,7 @@ res = {}
 for lib in libs:
     env = dict(os.environ)
     spec = lib.split(",")
+    env["DAD_TUNING"] = "1"
     env["DAD_LIB_PATH"] = os.path.join(ROOT, "dynamics_aware_diffusion_b200", spec[0])
     for kv in spec[1:]:
         k, v = kv.split("=")
