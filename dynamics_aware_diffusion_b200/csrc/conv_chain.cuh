@@ -154,10 +154,14 @@ conv_chain_kernel(const __grid_constant__ ChainArgs args) {
   uint64_t *empty_b = bars + 16;           // [CH_MAX_NB]
   uint64_t *tempty = bars + 24;            // [ACC]
   uint64_t *res_bar = bars + 28;           // [NWG]
-  // "accumulator ready" per consumer: unit u (the k-th unit of warpgroup w = u % NWG) completes ufull[w][k & 1], so
-  // every barrier is waited on in strictly consecutive phases by one warpgroup (conv_t3.cuh, parity aliasing)
-  uint64_t *ufull = bars + 32;             // [NWG][2]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 40);
+  // "accumulator ready" per consumer: unit u (the k-th unit of warpgroup w = u % NWG) completes ufull[w][k & 3], so
+  // every barrier is waited on in strictly consecutive phases by one warpgroup (conv_t3.cuh, parity aliasing).
+  // FOUR slots per warpgroup: a thread may sit in a dependency wait (the elected thread polling a tile counter) while
+  // the MMA warp keeps committing; at most ACC * UPI <= 8 units are in flight, a warpgroup owns every NWG-th of them,
+  // and units k and k + 4 (4 * NWG + 1 > 8 apart) can never be in flight together -- with two slots k and k + 2 can
+  // (NWG = 3), and a thread that misses two completions of one barrier waits for ever.
+  uint64_t *ufull = bars + 32;             // [NWG][4]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 48);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t cta_rank;
@@ -187,7 +191,7 @@ conv_chain_kernel(const __grid_constant__ ChainArgs args) {
       ptx::mbar_init(&full_b[s], 1);
       ptx::mbar_init(&empty_b[s], 1);
     }
-    for (int s = 0; s < 2 * NWG; ++s) ptx::mbar_init(&ufull[s], 1);
+    for (int s = 0; s < 4 * NWG; ++s) ptx::mbar_init(&ufull[s], 1);
     // every unit of the item is drained by 4 warps in each CTA of the pair
     for (int s = 0; s < ACC; ++s) ptx::mbar_init(&tempty[s], 8 * UPI);
     for (int s = 0; s < NWG; ++s) ptx::mbar_init(&res_bar[s], 1);
@@ -336,7 +340,7 @@ conv_chain_kernel(const __grid_constant__ ChainArgs args) {
 #pragma unroll
           for (int ns = 0; ns < UPI; ++ns) {
             const int u = it * UPI + ns, k = u / NWG;
-            ptx::umma_commit_2sm_mc(&ufull[(u - k * NWG) * 2 + (k & 1)], MC_MASK);
+            ptx::umma_commit_2sm_mc(&ufull[(u - k * NWG) * 4 + (k & 3)], MC_MASK);
           }
         }
         __syncwarp();
@@ -456,8 +460,8 @@ conv_chain_kernel(const __grid_constant__ ChainArgs args) {
       float ng = 0.f, ne = 0.f, nbi = 0.f, ntv = 0.f;
       if (have_next && wt < UC) load_col(nci, nitem, nns, ng, ne, nbi, ntv);
       {
-        uint64_t *bar = &ufull[wg * 2 + (k & 1)];
-        const uint32_t par = (uint32_t)(k >> 1) & 1u;
+        uint64_t *bar = &ufull[wg * 4 + (k & 3)];
+        const uint32_t par = (uint32_t)(k >> 2) & 1u;
         if (!ptx::mbar_try_wait(bar, par)) {
           // idle anyway: publish the completed store now (a consumer elsewhere may be waiting for exactly this tile)
           if (elected) publish_pending();

@@ -173,3 +173,25 @@ def test_full_width_dynamics_aware(name, precision):
         want = float(g["residual_dyn"][k])
         got = dynamics_residual(tr[k].cpu().numpy(), Pn, nz.obs_mean, nz.obs_std, nz.action_mean, nz.action_std, c["n"], c["m"])
         assert abs(got - want) <= (5e-5 if precision == "fp32" else 5e-2) * max(want, 1e-3), (k, got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_full_width_fusion_levels(name):
+    """conv_chain at these widths (GroupNorm width 128: 128-column units; width 256: two warpgroups share a group;
+    L = 4 bottleneck): one launch per conv, per block and per run of blocks give identical bits; the per-layer kernels
+    of round 1 (generic tcgen05 kernel for width 256, another summation order) agree to bf16 accuracy."""
+    c, g = helpers.FULL_CASES[name], helpers.load_golden(name)
+    dif = model(name, "bf16")
+    eng = dif.engine(c["H"], _dev())
+    gen = torch.Generator(device=_dev()).manual_seed(9)
+    x = torch.randn(21, c["H"], helpers.case_T(c), device=_dev(), generator=gen)     # ragged tiles, odd tile count
+    outs = {}
+    for level in (0, 1, 2, 3):
+        eng.set_fusion(level)
+        outs[level] = eng.unet_forward(x, step=1)
+        assert torch.equal(eng.unet_forward(x, step=1), outs[level]), "run-to-run variation at level %d" % level
+    eng.set_fusion(3)
+    assert bool(torch.isfinite(outs[3]).all())
+    assert torch.equal(outs[1], outs[2]) and torch.equal(outs[2], outs[3])
+    assert helpers.rel_l2(outs[0].cpu().numpy(), outs[3].cpu().numpy()) < 1e-2
