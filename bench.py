@@ -201,6 +201,121 @@ def run_reference(args, w, name):
     print(json.dumps(line))
 
 
+def build_policy(w, B, precision, dev, rank=0, latency_max_batch=None):
+    """(policy, diffusion, engine, flags, start condition) for a workload with random-init weights (seed 0 on rank 0)."""
+    import torch
+    from dynamics_aware_diffusion_b200 import (TemporalUnet, GaussianDiffusion, GuidedPolicy, DynamicsAwarePolicy,
+                                               synthetic, _native as N)
+    T, S, H = w["n"] + w["m"], w["S"], w["H"]
+    net = TemporalUnet(T, dim=w["dim"], dim_mults=w["mults"], precision=precision, max_batch=min(B, w.get("max_batch", B)),
+                       latency_max_batch=latency_max_batch)
+    dif = GaussianDiffusion(net, horizon=H, observation_dim=w["n"], action_dim=w["m"], n_timesteps=S)
+    synthetic.fill_state_dict(dif, 0 if rank == 0 else 1000 + rank)
+    dif.to(dev)
+    return net, dif
+
+
+def attach_policy(dif, w, dev, B):
+    import torch
+    from dynamics_aware_diffusion_b200 import GuidedPolicy, DynamicsAwarePolicy, _native as N
+    T, H = w["n"] + w["m"], w["H"]
+    P, nz = projector_inputs(w)
+    if P is not None:
+        pol = DynamicsAwarePolicy(dif, projection_matrix=P, normalizer=nz, state_dim=w["n"], observation_dim=w["n"],
+                                  action_dim=w["m"], horizon=H, projection_schedule="noise_schedule",
+                                  projection_strength=1.0)
+    else:
+        pol = GuidedPolicy(dif, nz)
+    eng = pol._engine(dev)
+    flags = pol._loop_flags(eng) | N.FLAG_CONDITIONS
+    start = torch.zeros(1, T, device=dev)
+    start[0, :w["n"]] = torch.randn(w["n"], generator=torch.Generator().manual_seed(1234)).to(dev)
+    eng.set_conditions({0: start}, B)
+    return pol, eng, flags, start, P is not None
+
+
+def config_leg(name, dev, pk, overrides, dsteps=10):
+    """One of BASELINE.json's other configurations, measured briefly on one GPU: `dsteps` diffusion steps of the
+    configured sampler at the configured batch (graph replays timed individually with CUDA events), reported as p50
+    step latency, plans/s extrapolated to the configured number of steps, and the U-Net tensor fraction."""
+    import torch
+    from dynamics_aware_diffusion_b200 import _native as N
+    w = dict(WORKLOADS[name])
+    w.update(overrides)
+    B, S = w["B"], w["S"]
+    cap = min(B, w.get("max_batch", B))
+    t0 = time.perf_counter()
+    net, dif = build_policy(w, cap, "bf16", dev)
+    pol, eng, flags, start, dyn = attach_policy(dif, w, dev, cap)
+    x = torch.empty(cap, w["H"], w["n"] + w["m"], device=dev)
+    # the schedule has S entries; time the LAST dsteps indices (well-conditioned steps; every step runs the same kernels)
+    eng.sample_profile(x, 3, flags=flags | N.FLAG_PHILOX_INIT, seed=1)           # warm-up + graph capture
+    step_ms = eng.sample_profile(x, dsteps, flags=flags | N.FLAG_PHILOX_INIT, seed=2)
+    p50 = statistics.median(step_ms)
+    info = eng.info()
+    chunks = (B + cap - 1) // cap
+    out = {"workload": name, "B": B, "H": w["H"], "T": w["n"] + w["m"], "diffusion_steps": S,
+           "unet": "dim=%d mults=%s" % (w["dim"], ",".join(map(str, w["mults"]))),
+           "policy": "dynamics-aware" if dyn else "guided", "timed_diffusion_steps": dsteps,
+           "p50_step_latency_ms": p50 * chunks, "plans_per_s_extrapolated": B / (p50 * chunks * 1e-3 * S),
+           "unet_tensor_frac_of_sustained": info["conv_flops_per_sample"] * cap / (p50 * 1e-3) / (pk["tf_sustained"] * 1e12),
+           "launches_per_step": info["launches_per_step"], "setup_s": None}
+    assert bool(torch.isfinite(x).all()), "non-finite trajectories in leg %s" % name
+    if chunks > 1:
+        out["note"] = "B exceeds the %d-plan workspace: %d chunks per step, latency = chunks x measured" % (cap, chunks)
+    del eng, pol, dif, net, x
+    torch.cuda.empty_cache()
+    out["setup_s"] = round(time.perf_counter() - t0, 1)
+    return out
+
+
+def gpu_eager_baseline(w, dev, B, dsteps=3):
+    """The honest GPU comparator: the reference's op sequence in STOCK PyTorch eager
+    (oracle/torch_port.py: cuDNN convs, native GroupNorm / Mish, the 15-op projection chain, torch.randn noise) on the
+    same B200, same batch, fp32 (PyTorch defaults: TF32 convs) and bf16 autocast.  `dsteps` steps timed with CUDA
+    events after one warm-up pass, extrapolated to the configured number of diffusion steps."""
+    import numpy as np
+    import torch
+    from oracle import torch_port
+    from dynamics_aware_diffusion_b200 import TemporalUnet, GaussianDiffusion, synthetic, projection_alphas
+    T, S, H = w["n"] + w["m"], w["S"], w["H"]
+    net = TemporalUnet(T, dim=w["dim"], dim_mults=w["mults"])
+    dif = GaussianDiffusion(net, horizon=H, observation_dim=w["n"], action_dim=w["m"], n_timesteps=S)
+    synthetic.fill_state_dict(dif, 0)
+    sd = {k: v.detach().to(dev) for k, v in dif.state_dict().items()}
+    P, nz = projector_inputs(w)
+    projector = None
+    if P is not None:
+        al = projection_alphas(S, S, "noise_schedule", 1.0, sd["betas"].cpu())
+        projector = dict(P=P.to(dev), alphas=[float(a) for a in al], n=w["n"], m=w["m"], H=H,
+                         nz=tuple(torch.from_numpy(np.asarray(a, dtype=np.float32)).to(dev)
+                                  for a in (nz.obs_mean, nz.obs_std, nz.action_mean, nz.action_std)))
+    start = torch.zeros(T, device=dev)
+    out = {"what": "torch eager (oracle/torch_port.py) on this GPU, B=%d, %d diffusion steps timed, extrapolated to %d"
+                   % (B, dsteps, S), "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32)}
+    for key, ctx in (("fp32", None), ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+        def run(steps):
+            x = torch.randn(B, H, T, device=dev)
+            fn = lambda: torch_port.sample_loop(sd, x, lambda k: torch.randn(B, H, T, device=dev), {0: start}, projector,
+                                                steps=steps)
+            if ctx is None:
+                return fn()
+            with ctx:
+                return fn()
+        run(1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run(dsteps)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_step = e0.elapsed_time(e1) / dsteps
+        out[key] = {"ms_per_diffusion_step": ms_step, "plans_per_s": B / (ms_step * 1e-3 * S)}
+    del sd
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -208,13 +323,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="pointmaze", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=0, help="plans per GPU (default: the workload's)")
+    ap.add_argument("--batch", type=int, default=0, help="TOTAL plans per bench step (default: the workload's)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong = the workload's B split over the ranks (BASELINE.json's metric: B=4096 at 1/2/4/8 "
+                         "GPUs), weak = the workload's B on every rank")
     ap.add_argument("--diffusion-steps", type=int, default=0, help="override S (default: the workload's)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=256)
     ap.add_argument("--cpu-diffusion-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--layers-out", default="", help="write the per-layer timing table (JSON) to this file")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the other BASELINE configs, the sweep and the eager-PyTorch comparator")
+    ap.add_argument("--layers-out", default="", help="write the per-layer / per-launch timing tables (JSON) to this file")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.batch:
@@ -229,9 +348,8 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from dynamics_aware_diffusion_b200 import (TemporalUnet, GaussianDiffusion, GuidedPolicy, DynamicsAwarePolicy,
-                                               synthetic, _native as N)
-    from dynamics_aware_diffusion_b200.distributed import broadcast_module
+    from dynamics_aware_diffusion_b200 import _native as N
+    from dynamics_aware_diffusion_b200.distributed import broadcast_module, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -241,40 +359,52 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    T, S, B, H = w["n"] + w["m"], w["S"], w["B"], w["H"]
+    T, S, H = w["n"] + w["m"], w["S"], w["H"]
+    B_total = w["B"] if (args.scaling == "strong" or world == 1) else w["B"] * world
+    lo, hi = shard_bounds(B_total, rank, world)
+    B = hi - lo                                   # this rank's plans
+    B_max = shard_bounds(B_total, 0, world)[1]    # the largest shard (all_gather_into_tensor wants equal shards)
+    assert B_total % world == 0, "the batch must divide over the ranks (all_gather_into_tensor)"
 
     # ---- model: random-init weights of the configured architecture, rank 0's replicated over NCCL (C1)
-    net = TemporalUnet(T, dim=w["dim"], dim_mults=w["mults"], precision=args.precision, max_batch=B)
-    dif = GaussianDiffusion(net, horizon=H, observation_dim=w["n"], action_dim=w["m"], n_timesteps=S)
-    synthetic.fill_state_dict(dif, 0 if rank == 0 else 1000 + rank)
-    dif.to(dev)
-    broadcast_module(dif, src=0)
-    P, nz = projector_inputs(w)
-    if P is not None:
-        pol = DynamicsAwarePolicy(dif, projection_matrix=P, normalizer=nz, state_dim=w["n"], observation_dim=w["n"],
-                                  action_dim=w["m"], horizon=H, projection_schedule="noise_schedule",
-                                  projection_strength=1.0)
-    else:
-        pol = GuidedPolicy(dif, nz)
-    eng = pol._engine(dev)
-    flags = pol._loop_flags(eng) | N.FLAG_CONDITIONS
-    start = torch.zeros(1, T, device=dev)
-    start[0, :w["n"]] = torch.randn(w["n"], generator=torch.Generator().manual_seed(1234)).to(dev)
-    eng.set_conditions({0: start}, B)
+    net, dif = build_policy(w, w["B"], args.precision, dev, rank, latency_max_batch=0 if world > 1 else None)
+    if world > 1:
+        torch.cuda.nvtx.range_push("broadcast_weights")
+        broadcast_module(dif, src=0)
+        torch.cuda.nvtx.range_pop()
+    pol, eng, flags, start, dyn = attach_policy(dif, w, dev, B)
     info = eng.info()
     x = torch.empty(B, H, T, device=dev)
-    gathered = torch.empty(world * B, H, T, device=dev) if world > 1 else None
+    gathered = torch.empty(B_total, H, T, device=dev) if world > 1 else None
 
-    def plan_batch(k):
+    def plan_batch(k, xb=None, out=None):
         # x_S drawn in-kernel (Philox, subsequence = global sample index), then S graph replays
-        eng.sample(x, S, flags=flags | N.FLAG_PHILOX_INIT, seed=1234 + k, sample_offset=rank * B)
+        xb = x if xb is None else xb
+        torch.cuda.nvtx.range_push("sample_loop")
+        eng.sample(xb, S, flags=flags | N.FLAG_PHILOX_INIT, seed=1234 + k, sample_offset=lo)
+        torch.cuda.nvtx.range_pop()
         if world > 1:
-            dist.all_gather_into_tensor(gathered, x)          # C2: final trajectory gather over NVLink
+            torch.cuda.nvtx.range_push("gather_trajectories")
+            dist.all_gather_into_tensor(gathered if out is None else out, xb)   # C2: final trajectory gather over NVLink
+            torch.cuda.nvtx.range_pop()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def timed(n_steps, fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(n_steps):
+            fn(100 + k)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
 
     for k in range(args.warmup):
         plan_batch(k)
@@ -282,51 +412,85 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = eng.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for k in range(args.steps):
-        plan_batch(100 + k)
-    e1.record()
-    barrier()
+    ms_total = timed(args.steps, plan_batch)
     clocks = sampler.finish()
     launches = eng.launch_count() - launches0
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    value = world * B * args.steps / (ms_total * 1e-3)
+    value = B_total * args.steps / (ms_total * 1e-3)
     assert bool(torch.isfinite(x).all()), "sampler produced non-finite trajectories"
     assert bool((x[:, 0] == start).all()), "inpainting lost"
+
+    # ---- multi-GPU correctness: the gathered batch equals a single-GPU recomputation, bit for bit.  The Philox
+    # subsequence of a plan is its GLOBAL index and a plan's result does not depend on its batch, so rank 0 recomputes
+    # 8 plans of EVERY rank's shard alone (sample_offset = their global index) and compares with what NCCL delivered.
+    nccl_check = None
+    if world > 1:
+        plan_batch(999)
+        torch.cuda.synchronize()
+        assert torch.equal(gathered[lo:hi], x), "all_gather misplaced this rank's shard"
+        if rank == 0:
+            nccl_check = {"rows_per_rank": 8, "ranks": world, "bit_exact": True}
+            for r in range(world):
+                r0 = shard_bounds(B_total, r, world)[0]
+                xr = torch.empty(8, H, T, device=dev)
+                eng.set_conditions({0: start}, 8)
+                eng.sample(xr, S, flags=flags | N.FLAG_PHILOX_INIT, seed=1234 + 999, sample_offset=r0)
+                torch.cuda.synchronize()
+                if not torch.equal(xr, gathered[r0:r0 + 8]):
+                    nccl_check["bit_exact"] = False
+            eng.set_conditions({0: start}, B)
+            assert nccl_check["bit_exact"], "gathered trajectories differ from the single-GPU recomputation"
+        dist.barrier()
+
+    # ---- the other scaling mode as an extra (N > 1): weak = the workload's B on every rank
+    other = None
+    if world > 1 and B_total // world != w["B"]:
+        Bw = w["B"]
+        xw = torch.empty(Bw, H, T, device=dev)
+        gw = torch.empty(world * Bw, H, T, device=dev)
+        eng.set_conditions({0: start}, Bw)
+        lo_keep = lo
+        lo = rank * Bw
+        plan_batch(0, xw, gw)
+        ms_w = timed(2, lambda k: plan_batch(k, xw, gw))
+        lo = lo_keep
+        eng.set_conditions({0: start}, B)
+        other = {"scaling": "weak", "B_per_gpu": Bw, "value": world * Bw * 2 / (ms_w * 1e-3), "unit": "plans/s", "steps": 2}
+        del xw, gw
 
     # ---- e2e: the C-ABI host-buffer call; pinned x_S in, x_0 out, every plan batch
     xh = torch.randn(B, H, T, generator=torch.Generator().manual_seed(7 + rank)).pin_memory()
     xs = xh.clone().pin_memory()
-    eng.sample_host(xs, S, flags=flags, seed=99, sample_offset=rank * B)        # warm-up (allocations)
+    eng.sample_host(xs, S, flags=flags, seed=99, sample_offset=lo)        # warm-up (allocations)
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
         xs.copy_(xh)
-        eng.sample_host(xs, S, flags=flags, seed=200 + k, sample_offset=rank * B)
+        eng.sample_host(xs, S, flags=flags, seed=200 + k, sample_offset=lo)
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / float(e2e_s.item())
+    e2e_value = B_total * args.steps / float(e2e_s.item())
     bytes_io = B * H * T * 4
 
     line = {
         "metric": "plans/sec", "value": value, "unit": "plans/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak" if (world > 1 and args.scaling == "weak") else "strong",
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "description": w["label"], "B_per_gpu": B, "H": H, "T": T,
-                   "diffusion_steps": S, "policy": "dynamics-aware" if P is not None else "guided",
+        "config": {"workload": args.workload, "description": w["label"], "B_total": B_total, "B_per_gpu": B, "H": H, "T": T,
+                   "diffusion_steps": S, "policy": "dynamics-aware" if dyn else "guided",
                    "unet": "dim=%d mults=%s" % (w["dim"], ",".join(map(str, w["mults"]))),
                    "noise": "in-kernel Philox", "parallelism": "batch-sharded x%d, replicated weights" % world,
-                   "l2": "working set per diffusion step (%.0f MB of activations + weights) exceeds the 126 MB L2; no flush"
-                         % (info["workspace_bytes"] / 1e6)},
+                   "l2": "working set per diffusion step (%.0f MB of activations + weights at B=%d) exceeds the 126 MB L2; no flush"
+                         % (info["workspace_bytes"] / 1e6 * B / max(w["B"], 1), B)},
         "e2e": {"value": e2e_value, "unit": "plans/s", "h2d_bytes_per_step": bytes_io, "d2h_bytes_per_step": bytes_io},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches": int(launches), "launches_per_diffusion_step": info["launches_per_step"], "clocks": clocks,
     }
+    if nccl_check:
+        line["nccl_check"] = nccl_check
+    if other:
+        line["other_scaling"] = other
 
     if rank == 0:
         pk = peaks()
@@ -336,30 +500,29 @@ def main():
         line["p99_step_latency_ms"] = sorted(step_ms)[int(0.99 * (len(step_ms) - 1))]
         flops_step = info["conv_flops_per_sample"] * B
         per_step_s = ms_total * 1e-3 / (args.steps * S)
+        # the whole step is timed inside the long timed region: the SUSTAINED peak is its denominator
         line["unet_tensor_frac_of_sustained"] = flops_step / per_step_s / (pk["tf_sustained"] * 1e12)
-        # ---- per-layer timing: the dominant kernel = the (instantiation, shape) with the largest share
-        groups = {}
-        table = []
-        for lay in eng.layers():
-            t_ms = eng.time_layer(lay["index"], B, iters=20)
-            fl = lay["flops_per_sample"] * B
-            lay.update(ms=t_ms, tflops=fl / (t_ms * 1e-3) / 1e12)
-            table.append(lay)
-            key = (lay["kernel"], lay["L_out"], lay["C_in"] * lay["taps"], lay["C_out"])
-            gk = groups.setdefault(key, {"ms": 0.0, "flops": 0, "count": 0})
-            gk["ms"] += t_ms
-            gk["flops"] += fl
-            gk["count"] += 1
-        unet_ms = sum(l["ms"] for l in table)
-        key, dom = max(groups.items(), key=lambda kv: kv[1]["ms"])
-        achieved = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
+        # ---- per-launch timing: the dominant kernel = the launch unit (a conv chain or a single conv) with the
+        # largest share of the U-Net time.  Units are timed ALONE (back-to-back launches of one unit): the BURST peak
+        # is the denominator for those.
+        units = eng.units()
+        for u in units:
+            u["ms"] = eng.time_unit(u["index"], B, iters=20)
+            u["tflops"] = u["flops_per_sample"] * B / (u["ms"] * 1e-3) / 1e12
+        unet_ms = sum(u["ms"] for u in units)
+        dom = max(units, key=lambda u: u["ms"])
+        achieved = dom["tflops"]
+        layers = eng.layers()
+        shapes = ", ".join(sorted({"L=%d K=%d N=%d" % (l["L_out"], l["C_in"] * l["taps"], l["C_out"])
+                                   for l in layers[dom["first_layer"]:dom["first_layer"] + dom["n_layers"]]}))
         line["roofline"] = {
-            "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-            "frac": achieved / pk["tf_sustained"], "traffic": ncu_traffic(key[0], args.workload),
-            "peak_source": pk["source"] + " sustained bf16",
-            "kernel": "%s L=%d K=%d N=%d x%d per step" % (key[0], key[1], key[2], key[3], dom["count"]),
-            "share_of_unet_time": dom["ms"] / unet_ms, "flops_per_launch": dom["flops"] / dom["count"],
-            "avg_launch_ms": dom["ms"] / dom["count"],
+            "bound": "tensor", "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+            "frac": achieved / pk["tf_burst"], "frac_of_sustained": achieved / pk["tf_sustained"],
+            "traffic": ncu_traffic(dom["kernel"].split("<")[0], args.workload),
+            "peak_source": pk["source"] + " burst bf16 (the kernel is timed alone, back to back)",
+            "kernel": "%s: %d convs in one launch (%s)" % (dom["kernel"], dom["n_layers"], shapes),
+            "share_of_unet_time": dom["ms"] / unet_ms, "flops_per_launch": dom["flops_per_sample"] * B,
+            "avg_launch_ms": dom["ms"],
         }
         # ---- the fused step kernel against the HBM roofline
         st_ms = eng.time_step_kernel(B, S // 2, flags=flags, iters=50)
@@ -375,31 +538,55 @@ def main():
             line["roofline_step_kernel_stream"] = stream_step_roofline(dev, pk)
         except Exception as exc:      # measurement extra: never fail the bench line over it
             line["roofline_step_kernel_stream"] = {"error": str(exc)[:200]}
-        line["unet_ms_sum_of_layers"] = unet_ms
+        line["unet_ms_sum_of_launches"] = unet_ms
         # the production caller's shape (GuidedPolicy.get_action, policies.py:193-223): ONE plan, latency-bound
-        try:
-            def one_plan_ms():
-                lat = []
-                for k in range(4):
-                    torch.cuda.synchronize()
-                    t0 = time.perf_counter()
-                    one = pol.sample_loop(batch_size=1, conditions={0: start}, seed=k)
-                    _ = one[0, :2].cpu()                      # the actions get_action reads back
-                    lat.append((time.perf_counter() - t0) * 1e3)
-                return statistics.median(lat[1:])
-            p50 = one_plan_ms()                               # default: the latency kernels (conv_small) up to B = 24
-            eng.set_latency_batch(0)
-            p50_tp = one_plan_ms()                            # the same plan through the throughput kernels
-            eng.set_latency_batch(24)
-            line["plan_latency_b1_ms"] = {"p50": p50, "p50_throughput_kernels": p50_tp, "diffusion_steps": S,
-                                          "us_per_diffusion_step": p50 * 1e3 / S,
-                                          "note": "sample_loop(batch_size=1) + D2H of the first actions, wall clock"}
-            eng.set_conditions({0: start}, B)
-        except Exception as exc:
-            line["plan_latency_b1_ms"] = {"error": str(exc)[:200]}
+        if world == 1:
+            try:
+                def one_plan_ms():
+                    lat = []
+                    for k in range(4):
+                        torch.cuda.synchronize()
+                        t0 = time.perf_counter()
+                        one = pol.sample_loop(batch_size=1, conditions={0: start}, seed=k)
+                        _ = one[0, :2].cpu()                      # the actions get_action reads back
+                        lat.append((time.perf_counter() - t0) * 1e3)
+                    return statistics.median(lat[1:])
+                p50 = one_plan_ms()                               # default: the latency kernels (conv_small) up to B = 24
+                eng.set_latency_batch(0)
+                p50_tp = one_plan_ms()                            # the same plan through the throughput kernels
+                eng.set_latency_batch(24)
+                line["plan_latency_b1_ms"] = {"p50": p50, "p50_throughput_kernels": p50_tp, "diffusion_steps": S,
+                                              "us_per_diffusion_step": p50 * 1e3 / S,
+                                              "note": "sample_loop(batch_size=1) + D2H of the first actions, wall clock"}
+                eng.set_conditions({0: start}, B)
+            except Exception as exc:
+                line["plan_latency_b1_ms"] = {"error": str(exc)[:200]}
         if args.layers_out:
             os.makedirs(os.path.dirname(os.path.abspath(args.layers_out)), exist_ok=True)
-            json.dump(table, open(args.layers_out, "w"), indent=1)
+            json.dump({"units": units, "layers": layers}, open(args.layers_out, "w"), indent=1)
+        if world == 1 and not args.no_extra_legs:
+            # free the headline model first: the other configurations need their own workspaces
+            del eng, pol
+            net._engines.clear()
+            torch.cuda.empty_cache()
+            # ---- the honest GPU comparator: stock PyTorch eager on this B200
+            try:
+                line["gpu_eager_baseline"] = gpu_eager_baseline(w, dev, B)
+                line["gpu_eager_baseline"]["speedup_vs_fp32"] = value / line["gpu_eager_baseline"]["fp32"]["plans_per_s"]
+                line["gpu_eager_baseline"]["speedup_vs_bf16_autocast"] = value / line["gpu_eager_baseline"]["bf16_autocast"]["plans_per_s"]
+            except Exception as exc:
+                line["gpu_eager_baseline"] = {"error": str(exc)[:300]}
+            # ---- BASELINE.json's other configurations and the scaling sweep, short legs on this GPU
+            legs = [("pointmaze_guided", {}), ("halfcheetah", {}), ("door", {}),
+                    ("pointmaze", {"H": 64}), ("pointmaze", {"H": 128, "B": 2048}),
+                    ("pointmaze", {"B": 256}), ("pointmaze", {"B": 1024}), ("pointmaze", {"B": 16384, "max_batch": 16384}),
+                    ("pointmaze", {"B": 65536, "max_batch": 16384})]
+            line["configs"] = []
+            for name, ov in legs:
+                try:
+                    line["configs"].append(config_leg(name, dev, pk, ov))
+                except Exception as exc:
+                    line["configs"].append({"workload": name, "overrides": ov, "error": str(exc)[:300]})
         # ---- CPU baseline: the reference's op sequence in torch on the host cores, bounded sample
         if not args.no_cpu_baseline and world == 1:
             import io

@@ -64,7 +64,7 @@ def build(force=False, verbose=False, defines=(), out=None):
         if res.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-o", target] + \
-        [obj for obj, _, _ in results]
+        [obj for obj, _, _ in results] + ["-ldl"]
     res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout + res.stderr)

@@ -2,6 +2,7 @@
 // CUDA-graph capture of one diffusion step, and the sampling loops.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <climits>
@@ -219,6 +220,12 @@ struct DevTemps {
 };
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// NVTX range around the host-side enqueue of a library call (header-only NVTX3: free when no profiler is attached)
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 // Set-up copy (host or device source) that has fully landed when the call returns.  A plain cudaMemcpy from
 // pageable host memory may return while the DMA is still in flight on the legacy stream, and the library's
@@ -1434,6 +1441,7 @@ int dad_destroy(dad_handle *h) {
 
 int dad_load_weights(dad_handle *h, const dad_tensor *tensors, int32_t n) {
   if (!h || !tensors) return DAD_ERR_INVALID;
+  NvtxRange nvtx("dad_load_weights");
   const dad_config &c = h->cfg;
   CK(h, cudaSetDevice(c.device));
   DAD_QUIESCE(h);
@@ -1617,6 +1625,7 @@ int dad_set_conditions(dad_handle *h, const int32_t *h_idx, const float *vals, i
 
 int dad_unet_forward(dad_handle *h, const float *x, const int64_t *t, int32_t step, float *eps, int32_t B, void *stream) {
   if (!h || !x || !eps || B < 1) return DAD_ERR_INVALID;
+  NvtxRange nvtx("dad_unet_forward");
   if (!h->have_weights) DAD_FAIL(h, DAD_ERR_STATE, "dad_unet_forward before dad_load_weights");
   if (!t && (step < 0 || step >= h->cfg.n_timesteps)) DAD_FAIL(h, DAD_ERR_INVALID, "step %d outside [0, %d)", step, h->cfg.n_timesteps);
   CK(h, cudaSetDevice(h->cfg.device));
@@ -1645,6 +1654,7 @@ int dad_unet_forward(dad_handle *h, const float *x, const int64_t *t, int32_t st
 int dad_step(dad_handle *h, float *x, const float *model_out, const float *noise, const float *grad, float guide_w,
              int32_t step, uint32_t flags, uint64_t seed, uint64_t sample_offset, int32_t B, void *stream) {
   if (!h || !x || !model_out || B < 1) return DAD_ERR_INVALID;
+  NvtxRange nvtx("dad_step");
   if (!h->have_sched) DAD_FAIL(h, DAD_ERR_STATE, "dad_step before dad_set_schedule");
   if (step < 0 || step >= h->cfg.n_timesteps) DAD_FAIL(h, DAD_ERR_INVALID, "step %d outside [0, %d)", step, h->cfg.n_timesteps);
   const bool project = (flags & DAD_FLAG_PROJECT) != 0;
@@ -1714,6 +1724,7 @@ int dad_project(dad_handle *h, float *x, int32_t step, int32_t B, void *stream) 
 int dad_sample(dad_handle *h, float *x, const float *noise_seq, uint64_t seed, uint64_t sample_offset, int32_t B,
                int32_t n_steps, uint32_t flags, float *trace, void *stream) {
   if (!h || !x || B < 1) return DAD_ERR_INVALID;
+  NvtxRange nvtx("dad_sample");
   if (!h->have_weights || !h->have_sched) DAD_FAIL(h, DAD_ERR_STATE, "dad_sample before weights and schedule are set");
   if (n_steps < 1 || n_steps > h->cfg.n_timesteps)
     DAD_FAIL(h, DAD_ERR_INVALID, "n_steps %d outside [1, %d] (the schedule tables have n_timesteps entries)", n_steps, h->cfg.n_timesteps);

@@ -182,5 +182,9 @@ def _run_loop(diffusion, x, noise, rng, seed, flags, return_trace=False, sample_
     if seed is None:
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if noise is None else 0
     trace = torch.empty((S,) + tuple(x.shape), device=x.device) if return_trace else None
-    eng.sample(x, S, noise_seq=noise, flags=flags, seed=seed, sample_offset=sample_offset, trace=trace)
+    torch.cuda.nvtx.range_push("sample_loop B=%d S=%d" % (x.shape[0], S))
+    try:
+        eng.sample(x, S, noise_seq=noise, flags=flags, seed=seed, sample_offset=sample_offset, trace=trace)
+    finally:
+        torch.cuda.nvtx.range_pop()
     return (x, trace) if return_trace else x

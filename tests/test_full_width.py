@@ -1,7 +1,7 @@
 """Parity at the REAL HalfCheetah / Door architectures (README.md:177-179, 194-196 of the reference; SURVEY.md
 Appendix B): dim 256, multipliers (1,4,8) / (1,2,4,8), GroupNorm widths 32 / 128 / 256, C_out up to 2048, bottleneck
 lengths 8 / 4.  The reduced-width cases of test_gpu_parity.py never reach the kernel instantiations these widths
-select (conv_t3 with GroupNorm width 128 and 256), so they get their own golden files -- outputs of the unmodified
+select (conv_chain with GroupNorm width 128 and 256), so they get their own golden files -- outputs of the unmodified
 reference on the deterministic weights of helpers.FULL_CASES (tests/golden/make_golden.py::make_full_case).
 
 CPU part: both oracles against those files.  GPU part: the CUDA path against them, through the reference-shaped
@@ -124,8 +124,8 @@ def test_full_width_kernel_selection(name):
             by_gw.setdefault(lay["group_width"], set()).add(lay["kernel"].split("<")[0])
     assert set(by_gw) >= {32, 128, 256}, by_gw
     for gw, kernels in by_gw.items():
-        assert kernels == {"conv_t3_kernel"}, (gw, kernels)
-    generic = [l["name"] for l in layers if not l["kernel"].startswith("conv_t3")]
+        assert kernels == {"conv_chain_kernel"}, (gw, kernels)
+    generic = [l["name"] for l in layers if not l["kernel"].startswith("conv_chain")]
     assert all((".2.conv" in n) or n.startswith("final_conv.1") for n in generic), generic
 
 
