@@ -19,7 +19,7 @@ EXPORTS = (
     "dad_set_schedule", "dad_set_projector", "dad_set_conditions", "dad_unet_forward", "dad_step",
     "dad_project", "dad_sample", "dad_sample_host", "dad_get_info", "dad_launch_count", "dad_set_latency_batch",
     "dad_loop_begin", "dad_loop_unet", "dad_loop_step", "dad_graph_epoch", "dad_loop_replayed",
-    "dad_build_projection_matrix",
+    "dad_build_projection_matrix", "dad_fit_linear_dynamics", "dad_dynamics_residual",
     "dad_sample_profile", "dad_layer_count", "dad_layer_info", "dad_time_layer", "dad_time_step_kernel",
     "dad_set_fusion", "dad_unit_count", "dad_unit_info", "dad_time_unit",
 )
@@ -104,6 +104,9 @@ def lib():
     L.dad_graph_epoch.restype = ctypes.c_int64
     L.dad_loop_replayed.argtypes = [vp, ctypes.c_int32]
     L.dad_build_projection_matrix.argtypes = [ctypes.c_int32, vp, ctypes.c_int32, ctypes.c_int32, vp]
+    L.dad_fit_linear_dynamics.argtypes = [ctypes.c_int32, vp, vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, vp, vp]
+    L.dad_dynamics_residual.argtypes = [ctypes.c_int32, vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                        vp, vp, vp, vp, vp, ctypes.POINTER(ctypes.c_double), vp]
     L.dad_sample_profile.argtypes = [vp, vp, u64, u64, i32, i32, u32, vp, vp]
     L.dad_layer_count.argtypes = [vp]
     L.dad_layer_info.argtypes = [vp, i32, ctypes.POINTER(DadLayerDesc)]

@@ -45,7 +45,10 @@ namespace dad {
 
 constexpr int CH_BN = 128;
 constexpr int CH_BK = 64;
-constexpr int CH_MAX_CONVS = 12;
+#ifndef DAD_CH_MAX_CONVS
+#define DAD_CH_MAX_CONVS 12
+#endif
+constexpr int CH_MAX_CONVS = DAD_CH_MAX_CONVS;
 constexpr int CH_MAX_NB = 8;          // weight-tile ring depth (runtime, <= 8)
 
 __host__ __device__ constexpr bool ch_narrow(int gw) { return gw == 16 || gw == 32; }

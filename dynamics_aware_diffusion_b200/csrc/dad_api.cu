@@ -1852,6 +1852,71 @@ int dad_build_projection_matrix(int32_t device, const double *F, int32_t rows, i
   return DAD_OK;
 }
 
+int dad_fit_linear_dynamics(int32_t device, const double *X, const double *U, const double *Xn, int64_t N, int32_t n,
+                            int32_t m, double *A, double *B) {
+  char buf[256];
+  if (!X || !U || !Xn || !A || !B || N < 1 || n < 1 || m < 1 || N < n + m) {
+    g_create_error = "dad_fit_linear_dynamics: bad arguments (need N >= n + m transitions)";
+    return DAD_ERR_INVALID;
+  }
+  cudaError_t e = cudaSetDevice(device);
+  int bad = 0;
+  if (e == cudaSuccess) e = fit_linear_dynamics_device(X, U, Xn, N, n, m, A, B, &bad);
+  if (e != cudaSuccess) {
+    snprintf(buf, sizeof(buf), "dad_fit_linear_dynamics: %s", cudaGetErrorString(e));
+    g_create_error = buf;
+    return DAD_ERR_CUDA;
+  }
+  if (bad) {
+    snprintf(buf, sizeof(buf), "dad_fit_linear_dynamics: [X U] is not of full column rank (pivot %d): the transitions do not identify (A, B)", bad);
+    g_create_error = buf;
+    return DAD_ERR_INVALID;
+  }
+  return DAD_OK;
+}
+
+int dad_dynamics_residual(int32_t device, const float *x, int32_t B, int32_t H, int32_t n, int32_t m, const float *P,
+                          const float *obs_mean, const float *obs_std, const float *act_mean, const float *act_std,
+                          double *out, void *stream) {
+  char buf[256];
+  if (!x || !P || !obs_mean || !obs_std || !act_mean || !act_std || !out || B < 1 || H < 1 || n < 1 || m < 1) {
+    g_create_error = "dad_dynamics_residual: bad arguments";
+    return DAD_ERR_INVALID;
+  }
+  cudaError_t e = cudaSetDevice(device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float *d_stats = nullptr;
+  double *d_out = nullptr;
+  std::vector<float> stats;
+  stats.insert(stats.end(), obs_mean, obs_mean + n);
+  stats.insert(stats.end(), obs_std, obs_std + n);
+  stats.insert(stats.end(), act_mean, act_mean + m);
+  stats.insert(stats.end(), act_std, act_std + m);
+  double sum = 0.0;
+  if (e == cudaSuccess) e = cudaMalloc(&d_stats, stats.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_stats, stats.data(), stats.size() * sizeof(float), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_out, 0, sizeof(double), st);
+  if (e == cudaSuccess) {
+    ResidualParams p{};
+    p.x = x; p.P = P; p.stats = d_stats; p.out = d_out;
+    p.B = B; p.H = H; p.n = n; p.m = m; p.T = n + m; p.Dc = (H + 1) * n + H * m;
+    residual_kernel<<<dim3((p.Dc + RS_N - 1) / RS_N, (B + RS_S - 1) / RS_S), RS_N, 0, st>>>(p);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&sum, d_out, sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    *out = sum / ((double)B * (double)p.Dc);
+  }
+  cudaFree(d_stats);
+  cudaFree(d_out);
+  if (e != cudaSuccess) {
+    snprintf(buf, sizeof(buf), "dad_dynamics_residual: %s", cudaGetErrorString(e));
+    g_create_error = buf;
+    return DAD_ERR_CUDA;
+  }
+  return DAD_OK;
+}
+
 int dad_loop_replayed(dad_handle *h, int32_t n) {
   if (!h || n < 0) return DAD_ERR_INVALID;
   h->launches += h->loop_kernels * n;

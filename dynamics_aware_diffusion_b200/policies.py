@@ -296,6 +296,7 @@ class DynamicsAwarePolicy(GuidedPolicy):
             setattr(self, name, val)
         self._fold = None          # (Nmat, q) fp64, rebuilt when the matrix or the normaliser changes
         self._fold_tag, self._fold_serial = None, 0
+        self._P_device = None      # (matrix identity, fp32 copy of P on the sampling device) for dynamics_residual
 
     def _get_projection_alpha(self, t: int) -> float:
         betas = self.diffusion.betas if self.projection_schedule == "noise_schedule" else None
@@ -356,6 +357,19 @@ class DynamicsAwarePolicy(GuidedPolicy):
             return 0
         self._push_projector(eng)
         return N.FLAG_PROJECT | (N.FLAG_PROJECT_AFTER_INPAINT if self.project_after_inpaint else 0)
+
+    def dynamics_residual(self, x: torch.Tensor) -> float:
+        """The reference's dynamics-violation metric of trajectories x (ProjectionLoss.compute,
+        losses/__init__.py:161-186) against this policy's projector; one fused kernel when x lives on the GPU."""
+        from .projection import dynamics_residual
+        if not self._active():
+            raise RuntimeError("dynamics_residual needs a projection matrix and a normalizer")
+        if self._P_device is None or self._P_device[0] != self._projector_inputs_tag()[0] or self._P_device[1].device != x.device:
+            self._P_device = (self._projector_inputs_tag()[0],
+                              torch.as_tensor(self.projection_matrix, dtype=torch.float32).to(x.device).contiguous())
+        nz = self.normalizer
+        return dynamics_residual(x, self._P_device[1], nz.obs_mean, nz.obs_std, nz.action_mean, nz.action_std,
+                                 self.state_dim, self.action_dim)
 
     @torch.no_grad()
     def apply_projection(self, x: torch.Tensor, t: int) -> torch.Tensor:

@@ -2,6 +2,7 @@
 
   ProjectionMatrixBuilder   P = F pinv(F)            reference: m_diffuser/dynamics/projection.py:11-133
   fit_linear_dynamics       lstsq([X U], X+)          reference: m_diffuser/dynamics/data_driven.py:75-134
+  dynamics_residual         mean((tau - tau P)^2)     reference: m_diffuser/losses/__init__.py:161-186
   fold_projection           DynamicsAwarePolicy.apply_projection (guides/policies.py:409-485) as
                             y = x + alpha * (N x + q) on the flattened normalised trajectory
   projection_alphas         _get_projection_alpha for every step (guides/policies.py:358-383)
@@ -61,13 +62,28 @@ class ProjectionMatrixBuilder:
         return bool(torch.allclose(P @ P, P, atol=1e-4))
 
 
-def fit_linear_dynamics(states, actions, next_states, state_dim=None, verbose=False):
-    """Least-squares (A, B) with x+ ~ A x + B u."""
-    states, actions, next_states = (np.asarray(a, dtype=np.float64) for a in (states, actions, next_states))
+def fit_linear_dynamics(states, actions, next_states, state_dim=None, verbose=False, device=None):
+    """Least-squares (A, B) with x+ ~ A x + B u (data_driven.py:107-121).  `device` (extra, optional): a CUDA device --
+    the normal equations are then formed and solved there in fp64 (`dad_fit_linear_dynamics`: split-K Gram products +
+    Cholesky) instead of numpy's SVD lstsq; the default, None, is the reference's numpy path."""
+    states, actions, next_states = (np.ascontiguousarray(a, dtype=np.float64) for a in (states, actions, next_states))
     if state_dim is not None and states.shape[1] > state_dim:
-        states, next_states = states[:, :state_dim], next_states[:, :state_dim]
-    n = states.shape[1]
-    theta, *_ = np.linalg.lstsq(np.hstack([states, actions]), next_states, rcond=None)
+        states, next_states = (np.ascontiguousarray(states[:, :state_dim]),
+                               np.ascontiguousarray(next_states[:, :state_dim]))
+    n, m = states.shape[1], actions.shape[1]
+    if device is not None:
+        from . import _native as N
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise ValueError("device must be a CUDA device (the default, None, is the reference's numpy path)")
+        A = np.empty((n, n), dtype=np.float64)
+        B = np.empty((n, m), dtype=np.float64)
+        rc = N.lib().dad_fit_linear_dynamics(dev.index or 0, states.ctypes.data, actions.ctypes.data,
+                                             next_states.ctypes.data, states.shape[0], n, m, A.ctypes.data, B.ctypes.data)
+        N.check(None, rc)
+        theta = np.vstack([A.T, B.T])
+    else:
+        theta, *_ = np.linalg.lstsq(np.hstack([states, actions]), next_states, rcond=None)
     if verbose:
         resid = next_states - np.hstack([states, actions]) @ theta
         print("fit_linear_dynamics: R^2 = %.4f" % (1 - (resid ** 2).sum() / ((next_states - next_states.mean(0)) ** 2).sum()))
@@ -120,14 +136,33 @@ def fold_projection(P, obs_mean, obs_std, action_mean, action_std, state_dim, ac
 
 def dynamics_residual(x, P, obs_mean, obs_std, action_mean, action_std, state_dim, action_dim):
     """mean((tau - tau P)^2) in physical space for normalised trajectories x (B, H, T): the reference's dynamics
-    violation metric, ProjectionLoss.compute (m_diffuser/losses/__init__.py:161-186), numpy fp64."""
-    x = np.asarray(x, dtype=np.float64)
+    violation metric, ProjectionLoss.compute (m_diffuser/losses/__init__.py:161-186).
+    A CUDA tensor x is reduced on its device by one fused kernel (`dad_dynamics_residual`: tau is built from x on the
+    fly, fp32 products like the reference's torch matmul, fp64 sum); anything else goes through numpy in fp64."""
+    if torch.is_tensor(x) and x.is_cuda:
+        import ctypes
+        from . import _native as N
+        xc = x.detach().to(torch.float32).contiguous()
+        Pd = torch.as_tensor(P, dtype=torch.float32).to(xc.device).contiguous()
+        Bsz, H, T = xc.shape
+        if T != state_dim + action_dim or Pd.shape != ((H + 1) * state_dim + H * action_dim,) * 2:
+            raise ValueError("x is %s and P is %s: inconsistent with state_dim=%d, action_dim=%d"
+                             % (tuple(xc.shape), tuple(Pd.shape), state_dim, action_dim))
+        stats = [np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1)) for a in (obs_mean, obs_std, action_mean, action_std)]
+        out = ctypes.c_double()
+        with torch.cuda.device(xc.device):
+            rc = N.lib().dad_dynamics_residual(xc.device.index or 0, xc.data_ptr(), Bsz, H, state_dim, action_dim,
+                                               Pd.data_ptr(), *[a.ctypes.data for a in stats], ctypes.byref(out),
+                                               torch.cuda.current_stream().cuda_stream)
+        N.check(None, rc)
+        return float(out.value)
+    x = np.asarray(x.detach().cpu() if torch.is_tensor(x) else x, dtype=np.float64)
     B = x.shape[0]
     s = x[:, :, :state_dim] * np.asarray(obs_std, np.float64) + np.asarray(obs_mean, np.float64)
     a = x[:, :, state_dim:state_dim + action_dim] * np.asarray(action_std, np.float64) + np.asarray(action_mean, np.float64)
     s = np.concatenate([s, s[:, -1:, :]], axis=1)                       # duplicated last state (losses/__init__.py:153)
     c = np.concatenate([s.reshape(B, -1), a.reshape(B, -1)], axis=1)
-    return float(np.mean((c - c @ np.asarray(P, dtype=np.float64)) ** 2))
+    return float(np.mean((c - c @ np.asarray(P.detach().cpu() if torch.is_tensor(P) else P, dtype=np.float64)) ** 2))
 
 
 def projection_alphas(n_table, n_timesteps, schedule, strength, betas=None):

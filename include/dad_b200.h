@@ -208,6 +208,21 @@ int dad_loop_replayed(dad_handle *h, int32_t n);
  * DAD_ERR_INVALID and dad_last_error(NULL) names the failing pivot.  No handle needed. */
 int dad_build_projection_matrix(int32_t device, const double *F, int32_t rows, int32_t cols, float *P);
 
+/* ---- data-driven dynamics on the device -------------------------------------------------------------------
+ * fit_linear_dynamics (dynamics/data_driven.py:107-121): Theta = lstsq([X U], X+), A = Theta[:n]^T, B = Theta[n:]^T.
+ * X (N x n), U (N x m), Xn (N x n): fp64 row-major HOST arrays of N transitions; A (n x n), B (n x m): fp64
+ * row-major HOST outputs.  Normal equations + Cholesky in fp64 on `device`; DAD_ERR_INVALID when [X U] is rank
+ * deficient to working precision.  No handle needed. */
+int dad_fit_linear_dynamics(int32_t device, const double *X, const double *U, const double *Xn, int64_t N, int32_t n,
+                            int32_t m, double *A, double *B);
+/* ProjectionLoss.compute (losses/__init__.py:161-186), the dynamics-violation metric: mean((tau - tau P)^2) with
+ * tau = [unnormalised states, last one duplicated | unnormalised actions].  x: (B, H, n + m) normalised trajectories,
+ * DEVICE fp32; P: ((H+1) n + H m)^2 DEVICE fp32 row-major; the four statistics: HOST fp32 arrays of n / n / m / m
+ * entries; *out: HOST double.  One fused kernel on `stream`; synchronises it. */
+int dad_dynamics_residual(int32_t device, const float *x, int32_t B, int32_t H, int32_t n, int32_t m, const float *P,
+                          const float *obs_mean, const float *obs_std, const float *act_mean, const float *act_std,
+                          double *out, void *stream);
+
 /* ---- measurement hooks (bench.py; no reference counterpart) ------------------------------------ */
 
 /* dad_sample with Philox noise that also returns the device time of every diffusion step (CUDA events

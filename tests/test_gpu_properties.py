@@ -274,3 +274,78 @@ def test_get_action_end_to_end(kind):
     assert pol._engine(_dev()).launch_count() == launches
     pol.get_action(obs)                                       # buffer empty -> replans
     assert pol._engine(_dev()).launch_count() > launches and len(pol.action_buffer) == 3
+
+
+def test_two_policies_share_one_engine_without_stale_projector():
+    """Advisor finding (round 1): the native handle is shared by every policy built on one diffusion model; the
+    'projector currently loaded' tag lives on the engine, so alternating policies re-push their own N, q, alpha.  A new
+    `policy.projection_matrix` / normaliser rebuilds the folded map."""
+    from dynamics_aware_diffusion_b200 import (TemporalUnet, GaussianDiffusion, DynamicsAwarePolicy, ProjectionMatrixBuilder,
+                                               synthetic)
+    net = TemporalUnet(6, dim=64, dim_mults=(1, 2), precision="fp32", max_batch=16)
+    dif = GaussianDiffusion(net, horizon=16, observation_dim=4, action_dim=2, n_timesteps=10)
+    synthetic.fill_state_dict(dif, 0)
+    dif.to(_dev())
+    A, B = synthetic.double_integrator(0.1)
+    A2 = A.copy()
+    A2[0, 2] = 0.3
+    nz = synthetic.SyntheticNormalizer(4, 2)
+    P1 = ProjectionMatrixBuilder(A, B, 4, 2).get_projection_matrix(16)
+    P2 = ProjectionMatrixBuilder(A2, B, 4, 2).get_projection_matrix(16)
+    kw = dict(normalizer=nz, state_dim=4, observation_dim=4, action_dim=2, horizon=16)
+    pa = DynamicsAwarePolicy(dif, projection_matrix=P1, projection_schedule="constant", projection_strength=1.0, **kw)
+    pb = DynamicsAwarePolicy(dif, projection_matrix=P2, projection_schedule="linear", projection_strength=0.5, **kw)
+    assert pa._engine(_dev()) is pb._engine(_dev())
+
+    def run(pol):
+        torch.manual_seed(3)
+        return pol.sample_loop(batch_size=8, seed=11)
+
+    a1, b1 = run(pa), run(pb)
+    a2, b2 = run(pa), run(pb)            # A again AFTER B pushed its projector to the shared handle
+    assert torch.equal(a1, a2) and torch.equal(b1, b2)
+    assert not torch.equal(a1, b1)
+    # a fresh policy with A's settings gives A's result: nothing of B leaked
+    pc = DynamicsAwarePolicy(dif, projection_matrix=P1, projection_schedule="constant", projection_strength=1.0, **kw)
+    assert torch.equal(run(pc), a1)
+    # replacing the matrix of a live policy is honoured (dynamics that change online)
+    pa.projection_matrix = P2
+    a3 = run(pa)
+    pd = DynamicsAwarePolicy(dif, projection_matrix=P2, projection_schedule="constant", projection_strength=1.0, **kw)
+    assert torch.equal(a3, run(pd)) and not torch.equal(a3, a1)
+    x = torch.randn(4, 16, 6, device=_dev(), generator=torch.Generator(device=_dev()).manual_seed(1))
+    assert torch.equal(pa.apply_projection(x, 0), pd.apply_projection(x, 0))
+
+
+def test_weight_writes_through_data_are_seen():
+    """Advisor finding (round 1): EMA.apply_shadow / update_ema / NCCL broadcasts write parameters through `.data`
+    (`p.data = shadow`, `p.data.mul_()`, `p.data.copy_()`), which bumps no autograd version.  The engine must re-pack."""
+    from dynamics_aware_diffusion_b200 import TemporalUnet, GaussianDiffusion, synthetic
+    net = TemporalUnet(6, dim=64, dim_mults=(1, 2), precision="bf16", max_batch=8)
+    dif = GaussianDiffusion(net, horizon=16, observation_dim=4, action_dim=2, n_timesteps=10)
+    synthetic.fill_state_dict(dif, 0)
+    dif.to(_dev())
+    x = torch.randn(4, 16, 6, device=_dev(), generator=torch.Generator(device=_dev()).manual_seed(1))
+    t = torch.full((4,), 3, device=_dev(), dtype=torch.long)
+    base = dif.model(x, t)
+    p = next(net.parameters())
+    # (1) in place through .data
+    p.data.mul_(1.5)
+    scaled = dif.model(x, t)
+    assert not torch.equal(scaled, base)
+    # (2) rebinding .data (EMA.apply_shadow), then restoring the original values
+    shadow = p.data / 1.5
+    p.data = shadow
+    assert helpers.rel_l2(dif.model(x, t).cpu().numpy(), base.cpu().numpy()) < 1e-2
+    # (3) the explicit hook
+    with torch.no_grad():
+        for q in net.parameters():
+            q.data.copy_(q.data * 1.0)
+    net.invalidate()
+    assert bool(torch.isfinite(dif.model(x, t)).all())
+    # out-of-range and non-integer timesteps are rejected instead of reading outside the tables
+    with pytest.raises(IndexError):
+        dif.model(x, torch.full((4,), 10, device=_dev(), dtype=torch.long))
+    with pytest.raises(ValueError):
+        dif.model(x, torch.full((4,), 2.5, device=_dev()))
+    assert torch.equal(dif.model(x, torch.full((4,), 3.0, device=_dev())), dif.model(x, t))
