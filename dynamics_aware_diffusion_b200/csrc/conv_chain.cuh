@@ -17,9 +17,9 @@
 // (conv, sample tile) has a counter in global memory:
 //
 //   producer side  epilogue warpgroup: TMA store of an output unit -> cp.async.bulk.wait_group (completion, not
-//                  just .read) -> fence.proxy.async -> red.release.gpu.add counter[conv][tile]
+//                  just .read) -> fence.proxy.async.global -> red.release.gpu.add counter[conv][tile]
 //   consumer side  TMA-producer warp (activation operand) / epilogue (residual operand):
-//                  ld.acquire.gpu counter >= units_per_tile -> fence.proxy.async -> TMA load
+//                  ld.acquire.gpu counter >= units_per_tile -> fence.proxy.async.global -> TMA load
 //
 // Waits only ever point at a LOWER conv index, and the grid is sized to be co-resident (occupancy query on the
 // host), so the schedule cannot deadlock.  The counters are zeroed by stage_x_kernel, the first kernel of every
@@ -54,8 +54,10 @@ constexpr int CH_MAX_NB = 8;          // weight-tile ring depth (runtime, <= 8)
 __host__ __device__ constexpr bool ch_narrow(int gw) { return gw == 16 || gw == 32; }
 // Epilogue shape per GroupNorm width (measured per layer in round 1): the narrow Conv1dBlocks are bound
 // by the epilogue's critical path and take 4 warpgroups x 8-column TMEM chunks; the MMA-bound wide layers 3 x 16;
-// width 256 pairs two warpgroups on the two halves of a group.
-__host__ __device__ constexpr int ch_nwg(int gw) { return gw == 256 ? 2 : (ch_narrow(gw) ? 4 : 3); }
+// width 256 pairs two warpgroups on the two halves of a group; width 128 (C_out = 1024, K >= 5120: an item's MMAs take
+// ~20 us, its two 128-column units ~8 us each) also runs two, which frees 32 KB of staging memory for the L = 4
+// bottleneck of the four-level U-Nets.
+__host__ __device__ constexpr int ch_nwg(int gw) { return gw >= 128 ? 2 : (ch_narrow(gw) ? 4 : 3); }
 __host__ __device__ constexpr int ch_cw(int gw) { return ch_narrow(gw) ? 8 : 16; }
 __host__ __device__ constexpr int ch_threads(int gw) { return 64 + 128 * ch_nwg(gw); }
 __host__ __device__ constexpr int ch_unit_cols(int gw) { return gw >= 128 ? 128 : 64; }
@@ -85,6 +87,7 @@ struct ChainConvMeta {
 // descriptors may live without any tensormap-proxy fencing.
 struct alignas(128) ChainConv {
   CUtensorMap tmA1, tmA2, tmW, tmR, tmO;
+  CUtensorMap tmW1;            // weights boxed for 128-wide items (64 rows per CTA): the NS = 1 launch of a chain planned with NS = 2
   ChainConvMeta m;
 };
 
@@ -97,6 +100,7 @@ struct ChainParams {
   int n_mst;                   // sample tiles
   int n_tiles_n;               // items along N (128 * NS columns each); the same for every conv of the chain
   int a_stage_bytes, n_a_stages, b_stage_bytes, nb_stages;
+  int w_alt;                   // 1: this launch runs the NS = 1 instantiation of an NS = 2 chain (weights through tmW1)
   int debug;
 };
 
@@ -232,7 +236,7 @@ conv_chain_kernel(const __grid_constant__ ChainArgs args) {
         }
       }
     }
-    ptx::fence_proxy_async_all();
+    ptx::fence_proxy_async_global();
   };
 
   // The producer and MMA warps stay CONVERGED: all 32 lanes walk the loops with warp-uniform values and only
@@ -254,6 +258,7 @@ conv_chain_kernel(const __grid_constant__ ChainArgs args) {
       const int tm = gm * 2 + (int)cta_rank;
       const int b0 = tm * p.S_t, n0 = tn * BN_ITEM;
       const int kch = cm.kch1 + cm.kch2;
+      const CUtensorMap *wmap = (NS == 1 && p.w_alt) ? &cv->tmW1 : &cv->tmW;
       // the activation tile of this entry was written by an earlier conv of this launch: wait for all its units
       if (cm.flag_a != nullptr && tm < p.n_mst) {
         if (leader_lane) wait_tile(cm.flag_a + tm, (uint32_t)cm.need_a * flag_mul);
@@ -277,7 +282,7 @@ conv_chain_kernel(const __grid_constant__ ChainArgs args) {
           if (leader_lane) {
             // this CTA keeps its half of the item's output channels; the pair MMA reads both halves
             if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_b[sb], 2u * (uint32_t)p.b_stage_bytes);
-            ptx::tma_load_2d_2sm(wdst, &cv->tmW, lead_full_b + 8u * sb, k0, n0 + (int)cta_rank * (BN_ITEM / 2));
+            ptx::tma_load_2d_2sm(wdst, wmap, lead_full_b + 8u * sb, k0, n0 + (int)cta_rank * (BN_ITEM / 2));
           }
           if (++sb == p.nb_stages) { sb = 0; phb ^= 1; }
         }
@@ -382,7 +387,7 @@ conv_chain_kernel(const __grid_constant__ ChainArgs args) {
     auto publish_pending = [&]() {                // elected thread: all stores of this warpgroup have completed
       if (pend_flag) {
         ptx::bulk_wait0();
-        ptx::fence_proxy_async_all();
+        ptx::fence_proxy_async_global();
         ptx::red_release_gpu_add(pend_flag, 1u);
         pend_flag = nullptr;
       }
@@ -408,7 +413,7 @@ conv_chain_kernel(const __grid_constant__ ChainArgs args) {
     auto release_acc = [&](int as) {
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(tempty0 + 8u * as);
+      if (lane == 0) ptx::mbar_arrive_remote(tempty0 + 8u * as);
     };
     // (gamma, beta, bias, time bias) of one column of a unit, straight from global memory (L2-resident tables)
     auto load_col = [&](int ci, int item, int ns, float &g, float &e, float &bi, float &tv) {
@@ -657,7 +662,7 @@ conv_chain_kernel(const __grid_constant__ ChainArgs args) {
           // the PREVIOUS store of this warpgroup was issued a whole unit ago: it has completed by now, publish it
           if (pend_flag) {
             ptx::bulk_wait1();
-            ptx::fence_proxy_async_all();
+            ptx::fence_proxy_async_global();
             ptx::red_release_gpu_add(pend_flag, 1u);
           }
           pend_flag = cm.flag_out ? cm.flag_out + tm : nullptr;

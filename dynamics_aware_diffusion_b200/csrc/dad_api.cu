@@ -83,6 +83,11 @@ struct ChainUnit {
   std::vector<int> ops;             // indices into dad_handle::ops, in execution order
   int GW = 0, MH = 1, NS = 1, L = 0, S_t = 0;
   int smem = 0, max_clusters = 0;
+  // launches with few work items (small batches) run 128-wide items instead of 256-wide ones: twice the entries, half
+  // the MMA time on each one's critical path (conv_t3's "half entries").  Ring depths / shared memory of that variant:
+  bool has_alt = false;
+  int alt_smem = 0, alt_max_clusters = 0, alt_n_a = 0, alt_nb = 0;
+  int main_n_a = 0, main_nb = 0;
   ChainArgs args{};
 };
 
@@ -656,8 +661,9 @@ std::string block_stem(const ConvOp &op) {
   return pos == std::string::npos ? op.wname : op.wname.substr(0, pos);
 }
 
-// Shared memory and ring depths of a chain; false when even the smallest configuration does not fit.
-bool chain_config(const dad_handle *h, ChainUnit &cu) {
+// Shared memory and ring depths of a chain run with `ns`-wide items; false when even the smallest configuration does
+// not fit.
+bool chain_config_ns(const dad_handle *h, const ChainUnit &cu, int ns, int *a_stage_out, int *n_a, int *nb, int *smem) {
   int a_stage = 0;
   for (int oi : cu.ops) {
     const ConvGeom &g = h->ops[oi].g;
@@ -666,22 +672,33 @@ bool chain_config(const dad_handle *h, ChainUnit &cu) {
     const int bytes = (cu.L + hi - lo) * cu.S_t * 128;
     a_stage = std::max(a_stage, (bytes + 1023) / 1024 * 1024);
   }
-  const int b_stage = cu.NS * 8192;
+  const int b_stage = ns * 8192;
   // deepest weight ring first (the MMA issue rate depends on it), then as many activation stages as still fit
   static const int combos[][2] = {{4, 6}, {3, 6}, {2, 6}, {3, 5}, {2, 5}, {3, 4}, {2, 4}, {2, 3}};
   for (auto &c : combos) {
     const ChSmem lay = ch_smem_layout(a_stage, c[0], b_stage, c[1], cu.S_t, cu.GW);
     if (lay.total <= h->max_smem_optin) {
-      ChainParams &p = cu.args.p;
-      p.a_stage_bytes = a_stage;
-      p.n_a_stages = c[0];
-      p.b_stage_bytes = b_stage;
-      p.nb_stages = c[1];
-      cu.smem = lay.total;
+      *a_stage_out = a_stage;
+      *n_a = c[0];
+      *nb = c[1];
+      *smem = lay.total;
       return true;
     }
   }
   return false;
+}
+
+bool chain_config(const dad_handle *h, ChainUnit &cu) {
+  int a_stage, n_a, nb, smem;
+  if (!chain_config_ns(h, cu, cu.NS, &a_stage, &n_a, &nb, &smem)) return false;
+  ChainParams &p = cu.args.p;
+  p.a_stage_bytes = a_stage;
+  cu.main_n_a = n_a;
+  cu.main_nb = nb;
+  cu.smem = smem;
+  cu.has_alt = false;
+  if (cu.NS == 2 && cu.GW != 256 && chain_config_ns(h, cu, 1, &a_stage, &cu.alt_n_a, &cu.alt_nb, &cu.alt_smem)) cu.has_alt = true;
+  return true;
 }
 
 // Tensor maps, scalars and dependency counters of every conv of the chain.
@@ -695,6 +712,7 @@ int finish_chain(dad_handle *h, ChainUnit &cu, int unit_index) {
   p.L = cu.L;
   p.S_t = cu.S_t;
   p.n_tiles_n = h->ops[cu.ops[0]].g.Cout / (CH_BN * cu.NS);
+  p.w_alt = 0;
   p.debug = 0;
   // which act is produced by which conv of this chain
   std::map<int, int> producer;
@@ -716,6 +734,8 @@ int finish_chain(dad_handle *h, ChainUnit &cu, int unit_index) {
     cuuint64_t strides[1] = {K * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)(64 * cu.NS)};         // each CTA of the pair keeps half of the item's rows
     if ((rc = make_tmap_raw(h, &cv.tmW, op.w_b16, 2, dims, strides, box, "chain weights"))) return rc;
+    cuuint32_t box1[2] = {64, 64};
+    if ((rc = make_tmap_raw(h, &cv.tmW1, op.w_b16, 2, dims, strides, box1, "chain weights (128-wide items)"))) return rc;
     const int pph = 128 / cu.S_t;
     if ((rc = make_t3_act_tmap(h, &cv.tmO, op.out, cu.S_t, pph, "chain output"))) return rc;
     if ((rc = make_t3_act_tmap(h, &cv.tmR, op.res >= 0 ? op.res : op.out, cu.S_t, pph, "chain residual"))) return rc;
@@ -761,6 +781,12 @@ int finish_chain(dad_handle *h, ChainUnit &cu, int unit_index) {
   CK(h, ops->max_clusters(cu.MH, cu.NS, cu.smem, &cu.max_clusters));
   cu.max_clusters = std::min(cu.max_clusters, h->sm_count / 2);
   if (cu.max_clusters < 1) DAD_FAIL(h, DAD_ERR_CUDA, "conv_chain_kernel<GW=%d> cannot be resident with %d bytes of shared memory", cu.GW, cu.smem);
+  if (cu.has_alt) {
+    CK(h, ops->prepare(cu.MH, 1, h->max_smem_optin));
+    CK(h, ops->max_clusters(cu.MH, 1, cu.alt_smem, &cu.alt_max_clusters));
+    cu.alt_max_clusters = std::min(cu.alt_max_clusters, h->sm_count / 2);
+    if (cu.alt_max_clusters < 1) cu.has_alt = false;
+  }
   return DAD_OK;
 }
 
@@ -830,11 +856,24 @@ int enqueue_chain(dad_handle *h, ChainUnit &cu, int B, cudaStream_t st, int flag
   p.B = B;
   p.n_mst = cdiv(B, cu.S_t);
   p.flag_epoch = flag_epoch;
+  const int cout = h->ops[cu.ops[0]].g.Cout;
+  // 256-wide items are the efficient shape (1,610 vs ~1,100 TFLOP/s of MMA issue) when there are rounds of them; when
+  // ALL of a conv's 256-wide items would occupy at most half of the clusters, 128-wide items put twice the clusters to
+  // work and halve the MMA time on every item's critical path
+  const int items2 = cdiv(p.n_mst, 2) * (cout / (CH_BN * cu.NS));
+  const bool alt = cu.has_alt && 2 * items2 <= cu.alt_max_clusters;
+  const int ns = alt ? 1 : cu.NS;
+  p.n_tiles_n = cout / (CH_BN * ns);
+  p.w_alt = alt ? 1 : 0;
+  p.b_stage_bytes = ns * 8192;
+  p.n_a_stages = alt ? cu.alt_n_a : cu.main_n_a;
+  p.nb_stages = alt ? cu.alt_nb : cu.main_nb;
+  const int smem = alt ? cu.alt_smem : cu.smem;
   const int entries = cdiv(p.n_mst, 2) * p.n_tiles_n * p.n_convs;
   // persistent, and never more clusters than can be co-resident: a cluster spins on tiles that other clusters of
   // this launch produce
-  const int n_cl = std::min(entries, cu.max_clusters);
-  cudaError_t e = chain_ops(cu.GW)->launch(cu.MH, cu.NS, 2 * n_cl, cu.smem, st, cu.args);
+  const int n_cl = std::min(entries, alt ? cu.alt_max_clusters : cu.max_clusters);
+  cudaError_t e = chain_ops(cu.GW)->launch(cu.MH, ns, 2 * n_cl, smem, st, cu.args);
   if (e != cudaSuccess) DAD_FAIL(h, DAD_ERR_CUDA, "conv_chain launch failed (%s ...): %s", h->ops[cu.ops[0]].wname.c_str(), cudaGetErrorString(e));
   h->counting += 1;
   return DAD_OK;

@@ -67,8 +67,9 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
 __device__ __forceinline__ void red_release_gpu_add(uint32_t *p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// orders generic-proxy and async-proxy (TMA) accesses of this thread, all state spaces (global included)
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// orders generic-proxy and async-proxy (TMA) accesses of this thread to GLOBAL memory (one FENCE.VIEW.ASYNC.G; the
+// unqualified form adds a MEMBAR.ALL.GPU)
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -133,6 +134,12 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local_saddr, uint32_t rank) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+// Remote arrive with the default (.release.cta) semantics: enough when the barrier guards TENSOR MEMORY, whose
+// accesses are ordered by tcgen05.fence::before/after_thread_sync, not by the arrive.  The .release.cluster form above
+// costs a MEMBAR.ALL.GPU per call (seen in SASS and in the ncu stall samples of the epilogue warps).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap *m, uint32_t src_saddr, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"

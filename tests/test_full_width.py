@@ -17,6 +17,9 @@ NAMES = list(helpers.FULL_CASES)
 TOL = {"fp32": 1e-5, "bf16": 1e-2, "bf16-latency": 1e-2}
 EPS_TOL = {"fp32": 1e-5, "bf16": 1.5e-2, "bf16-latency": 1.5e-2}     # raw eps in bf16: see test_gpu_parity.EPS_TOL
 ILL_TOL = 5e-2                                                          # the one ill-conditioned step, test_gpu_parity.ILL_TOL
+# fp32 mode on that same step: d(mean)/d(eps) = 99.98, so two fp32 summation orders of a K = 20,480 convolution (ours vs
+# oneDNN's, ~1e-7 apart on eps) show up as 1.04e-5 on x at the full HalfCheetah width; every other step stays below 1e-5
+ILL_TOL_F32 = 3e-5
 
 _sd_cache = {}
 
@@ -92,7 +95,8 @@ def step_tols(c, sd, precision):
     out = []
     for i in reversed(range(c["S"])):
         amp = float(sd["posterior_mean_coef1"][i] * sd["sqrt_recipm1_alphas_cumprod"][i])
-        out.append(ILL_TOL if (precision.startswith("bf16") and amp > 10.0) else TOL[precision])
+        ill = amp > 10.0
+        out.append((ILL_TOL if precision.startswith("bf16") else ILL_TOL_F32) if ill else TOL[precision])
     return out
 
 
