@@ -21,7 +21,7 @@ EXPORTS = (
     "dad_loop_begin", "dad_loop_unet", "dad_loop_step", "dad_graph_epoch", "dad_loop_replayed",
     "dad_build_projection_matrix", "dad_fit_linear_dynamics", "dad_dynamics_residual",
     "dad_sample_profile", "dad_layer_count", "dad_layer_info", "dad_time_layer", "dad_time_step_kernel",
-    "dad_set_fusion", "dad_unit_count", "dad_unit_info", "dad_time_unit",
+    "dad_set_fusion", "dad_unit_count", "dad_unit_info", "dad_time_unit", "dad_debug_counters",
 )
 
 
@@ -112,6 +112,7 @@ def lib():
     L.dad_layer_info.argtypes = [vp, i32, ctypes.POINTER(DadLayerDesc)]
     L.dad_time_layer.argtypes = [vp, i32, i32, i32, ctypes.POINTER(ctypes.c_float), vp]
     L.dad_time_step_kernel.argtypes = [vp, i32, i32, u32, i32, ctypes.POINTER(ctypes.c_float), vp]
+    L.dad_debug_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32 * 4), i32]
     L.dad_set_fusion.argtypes = [vp, i32]
     L.dad_unit_count.argtypes = [vp]
     L.dad_unit_info.argtypes = [vp, i32, ctypes.POINTER(DadUnitDesc)]

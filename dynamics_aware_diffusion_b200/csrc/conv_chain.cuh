@@ -235,7 +235,17 @@ conv_chain_kernel(const __grid_constant__ ChainArgs args) {
           __trap();
         }
       }
+#ifdef DAD_TUNING
+      // dependency-stall accounting (tools/chain_stalls.py): [1] = waits that had to spin, [2] = ns spent spinning
+      if (p.err) {
+        atomicAdd(p.err + 1, 1u);
+        atomicAdd(p.err + 2, (unsigned)(ptx::globaltimer_ns() - t0));
+      }
+#endif
     }
+#ifdef DAD_TUNING
+    if (p.err) atomicAdd(p.err + 3, 1u);                        // [3] = all dependency waits
+#endif
     ptx::fence_proxy_async_global();
   };
 
@@ -477,9 +487,10 @@ conv_chain_kernel(const __grid_constant__ ChainArgs args) {
         }
         __syncwarp();
       }
-      uint32_t t_addr[MH];
-#pragma unroll
-      for (int h = 0; h < MH; ++h) t_addr[h] = tmem_base + ((it * MH + h) % ACC) * BN_ITEM + ((uint32_t)(q * 32) << 16);
+      // TMEM address of this warp's lane quarter in accumulator half h (computed, not indexed: a [MH] array indexed
+      // by the rolled h loop of pass 2 lands in local memory)
+      const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+      auto t_addr_of = [&](int h) -> uint32_t { return t_lane + (uint32_t)(((it * MH + h) % ACC) * BN_ITEM); };
       ptx::tc_fence_after();
       if (!tile_ok) {
         // nothing to write for this tile (odd tile count): hand the accumulators back and move on
@@ -518,7 +529,7 @@ conv_chain_kernel(const __grid_constant__ ChainArgs args) {
 #pragma unroll
           for (int h = 0; h < MH; ++h) {
             uint32_t v[32];
-            if constexpr (CW == 16) ptx::tmem_ld16(t_addr[h] + col0 + c * CW, v); else ptx::tmem_ld8(t_addr[h] + col0 + c * CW, v);
+            if constexpr (CW == 16) ptx::tmem_ld16(t_addr_of(h) + col0 + c * CW, v); else ptx::tmem_ld8(t_addr_of(h) + col0 + c * CW, v);
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < CW / 2; ++j) {
@@ -561,6 +572,7 @@ conv_chain_kernel(const __grid_constant__ ChainArgs args) {
       // ---- pass 2: normalise, Mish, (+ time bias | + residual), convert, stage, TMA store
 #pragma unroll 1
       for (int h = 0; h < MH; ++h) {
+        const uint32_t t_h = t_addr_of(h) + col0;
         if (has_res) { ptx::mbar_wait(&res_bar[wg], res_phase); res_phase ^= 1; }
         f32x2 rg2[GPC], nm2[GPC];      // (rstd, -mean) of the current group(s), carried across the chunks of a wide group
 #pragma unroll
@@ -568,7 +580,7 @@ conv_chain_kernel(const __grid_constant__ ChainArgs args) {
 #pragma unroll 1
         for (int c = 0; c < NCHUNK; ++c) {
           uint32_t v[32];
-          if constexpr (CW == 16) ptx::tmem_ld16(t_addr[h] + col0 + c * CW, v); else ptx::tmem_ld8(t_addr[h] + col0 + c * CW, v);
+          if constexpr (CW == 16) ptx::tmem_ld16(t_h + c * CW, v); else ptx::tmem_ld8(t_h + c * CW, v);
           const uint32_t sp = pb + (uint32_t)((c * CW) >> 1) * 32u;
           f32x2 y[CW / 2];
           if (!plain) {

@@ -1452,8 +1452,8 @@ int dad_create(const dad_config *cfg, dad_handle **out) {
     const size_t words = h->ops.size() * (size_t)h->tiles_cap;
     if ((rc = dev_alloc(h, &h->d_flags, words))) return fail(rc);
     fill_now(h->d_flags, 0, words * sizeof(unsigned), h->own_stream);
-    if ((rc = dev_alloc(h, &h->d_err, 1))) return fail(rc);
-    fill_now(h->d_err, 0, sizeof(unsigned), h->own_stream);
+    if ((rc = dev_alloc(h, &h->d_err, 4))) return fail(rc);      // [0] error code; [1..3] stall counters of -DDAD_TUNING builds
+    fill_now(h->d_err, 0, 4 * sizeof(unsigned), h->own_stream);
     h->fusion = tuning_env("DAD_FUSION", h->fusion);
   } else {
     h->fusion = 0;
@@ -2136,6 +2136,17 @@ int dad_set_fusion(dad_handle *h, int32_t level) {
   drop_graphs(h);
   h->fusion = level;
   return build_units(h);
+}
+
+int dad_debug_counters(dad_handle *h, uint32_t *out4, int32_t reset) {
+  if (!h || !out4) return DAD_ERR_INVALID;
+  for (int i = 0; i < 4; ++i) out4[i] = 0;
+  if (!h->d_err) return DAD_OK;
+  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaDeviceSynchronize());
+  CK(h, cudaMemcpy(out4, h->d_err, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  if (reset) CK(h, cudaMemset(h->d_err, 0, 4 * sizeof(unsigned)));
+  return DAD_OK;
 }
 
 int dad_unit_count(const dad_handle *h) { return h ? (int)h->units.size() : 0; }

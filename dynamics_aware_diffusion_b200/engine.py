@@ -249,6 +249,13 @@ class Engine:
             self._ck(self.lib.dad_time_unit(self.handle, int(index), int(B), int(iters), ctypes.byref(ms), _stream()))
         return ms.value
 
+    def debug_counters(self, reset=False):
+        """(error code, waits that spun, ns spent spinning, all dependency waits) of the conv chains; the last three
+        are counted by -DDAD_TUNING builds only."""
+        out = (ctypes.c_uint32 * 4)()
+        self._ck(self.lib.dad_debug_counters(self.handle, ctypes.byref(out), 1 if reset else 0))
+        return tuple(int(v) for v in out)
+
     def set_fusion(self, level):
         """0 = per-layer kernels of round 1, 1 = chain kernel per conv, 2 = per ResidualTemporalBlock, 3 = per run of
         blocks (default)."""

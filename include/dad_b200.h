@@ -245,6 +245,10 @@ int dad_layer_info(const dad_handle *h, int32_t index, dad_layer_desc *out);
  * untimed launch); *ms_per_launch receives the average.  Operates on the handle's own workspaces (their
  * contents are whatever the last forward left there).  Synchronises. */
 int dad_time_layer(dad_handle *h, int32_t index, int32_t B, int32_t iters, float *ms_per_launch, void *stream);
+/* Device-side diagnostics of the conv chains: out4[0] = error code left by a dependency wait that timed out (0 = none);
+ * out4[1..3] = waits that had to spin / nanoseconds spent spinning / all dependency waits (counted by -DDAD_TUNING
+ * builds only, else 0).  Synchronises the device; `reset` clears the counters. */
+int dad_debug_counters(dad_handle *h, uint32_t *out4, int32_t reset);
 /* Launch units of one U-Net pass at the current fusion level: a conv chain (layers [first_layer, first_layer +
  * n_layers) in ONE launch) or a single layer. */
 typedef struct {
