@@ -78,6 +78,14 @@ class GaussianDiffusion(nn.Module):
         self.loss_type = loss_type
         # the stand-alone model(x, t) call shares the engine (and its time tables) with the sampling loop
         model._n_timesteps = int(betas.shape[0])
+        # bf16 models: evaluate the ILL-CONDITIONED leading reverse steps with the fp32 kernels.  With the cosine schedule
+        # beta_{S-1} is clipped to 0.9999 (diffusion.py:41), so the first reverse step has d(mean)/d(eps) = 99.98 and any
+        # bf16 evaluation of eps (ours 8e-3 relative, stock autocast 1.1e-2) shows up as 1.3-2e-2 on x at that one step;
+        # every other step amplifies eps errors by < 1.5.  True keeps every step within the 1e-2 bf16 tolerance at the
+        # price of ONE fp32 U-Net pass per sampling loop (fp32 SIMT kernels: ~40 bf16 steps' worth at B=4096); the
+        # default, False, runs every step on the tensor cores.
+        self.fp32_ill_conditioned_steps = False
+        self._ill_cache = None
 
     # ---- native plumbing ------------------------------------------------------------------------
     _SCHEDULE_BUFFERS = ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
@@ -88,18 +96,32 @@ class GaussianDiffusion(nn.Module):
         bufs = [getattr(self, n) for n in self._SCHEDULE_BUFFERS]
         return (tuple((b.data_ptr(), b._version) for b in bufs), float(torch.stack([b.double().sum() for b in bufs]).sum()))
 
-    def engine(self, horizon=None, device=None):
+    def engine(self, horizon=None, device=None, precision=None):
         """Native handle with this process's weights and schedule tables loaded (rebuilt lazily on change)."""
         device = device if device is not None else self.betas.device
         self.model._diffusion_cfg = dict(predict_epsilon=bool(self.predict_epsilon), clip_denoised=bool(self.clip_denoised))
         self.model._n_timesteps = int(self.betas.shape[0])
-        eng, ent = self.model.engine(horizon or self.horizon, device, n_timesteps=self.betas.shape[0])
+        eng, ent = self.model.engine(horizon or self.horizon, device, n_timesteps=self.betas.shape[0], precision=precision)
         tag = (id(self), self._schedule_version())
         if ent.get("schedule_owner") != tag:
             eng.set_schedule(self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod,
                              self.posterior_mean_coef1, self.posterior_mean_coef2, self.posterior_log_variance_clipped)
             ent["schedule_owner"] = tag
         return eng
+
+    def ill_conditioned_prefix(self, n_steps=None) -> int:
+        """How many LEADING reverse steps (i = S-1, S-2, ...) amplify an eps error by more than 10x:
+        d(mean)/d(eps) = posterior_mean_coef1[i] * sqrt_recipm1_alphas_cumprod[i].  1 for the cosine schedule, 0 for the
+        linear one."""
+        S = int(n_steps or self.n_timesteps)
+        tag = (self._schedule_version(), S)
+        if self._ill_cache is None or self._ill_cache[0] != tag:
+            amp = (self.posterior_mean_coef1 * self.sqrt_recipm1_alphas_cumprod).detach().cpu()[:S]
+            k = 0
+            while k < S and float(amp[S - 1 - k]) > 10.0:
+                k += 1
+            self._ill_cache = (tag, k)
+        return self._ill_cache[1]
 
     def _check_steps(self):
         if self.n_timesteps > self.betas.shape[0]:
@@ -184,7 +206,23 @@ def _run_loop(diffusion, x, noise, rng, seed, flags, return_trace=False, sample_
     trace = torch.empty((S,) + tuple(x.shape), device=x.device) if return_trace else None
     torch.cuda.nvtx.range_push("sample_loop B=%d S=%d" % (x.shape[0], S))
     try:
-        eng.sample(x, S, noise_seq=noise, flags=flags, seed=seed, sample_offset=sample_offset, trace=trace)
+        lead = 0
+        if diffusion.fp32_ill_conditioned_steps and eng.precision == "bf16":
+            # leading ill-conditioned steps: eps from the fp32 kernels, the rest of the step (and of the loop) unchanged.
+            # Philox slots and noise / trace slots are indexed by the step, so the split does not change the draws.
+            lead = diffusion.ill_conditioned_prefix(S)
+            if lead:
+                eng32 = diffusion.engine(x.shape[1], x.device, precision="fp32")
+                for k in range(lead):
+                    i = S - 1 - k
+                    eps = eng32.unet_forward(x, step=i)
+                    eng.step(x, eps, i, noise=None if noise is None else noise[k], flags=flags, seed=seed,
+                             sample_offset=sample_offset)
+                    if trace is not None:
+                        trace[k].copy_(x)
+        if S - lead > 0:
+            eng.sample(x, S - lead, noise_seq=None if noise is None else noise[lead:], flags=flags, seed=seed,
+                       sample_offset=sample_offset, trace=None if trace is None else trace[lead:])
     finally:
         torch.cuda.nvtx.range_pop()
     return (x, trace) if return_trace else x

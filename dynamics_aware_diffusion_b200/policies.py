@@ -107,6 +107,10 @@ class GuidedPolicy(nn.Module):
             flags |= N.FLAG_CONDITIONS
         guided = self.guide_fn is not None and self.guide_weight > 0
         if not guided:
+            if conditions and self.diffusion.fp32_ill_conditioned_steps:
+                # x_S is inpainted before the first model call (policies.py:137-138); dad_sample does it in-kernel, the
+                # fp32 pre-steps need it done here
+                x = self.apply_conditions(x, {h: torch.as_tensor(v, device=device) for h, v in conditions.items()})
             return _run_loop(self.diffusion, x, noise, rng, seed, flags, return_trace, sample_offset)
         # guided: autograd supplies the gradient each step, the rest stays native
         S = self.diffusion.n_timesteps

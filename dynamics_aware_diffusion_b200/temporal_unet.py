@@ -126,16 +126,18 @@ class TemporalUnet(nn.Module):
 
     refresh_weights = invalidate
 
-    def engine(self, horizon, device, n_timesteps=None, min_batch=1):
-        """The native handle for (horizon, device); rebuilt when shapes change, re-packed when weights change."""
+    def engine(self, horizon, device, n_timesteps=None, min_batch=1, precision=None):
+        """The native handle for (horizon, device); rebuilt when shapes change, re-packed when weights change.
+        `precision` overrides the module's (the fp32 sibling that evaluates ill-conditioned steps of a bf16 model)."""
         n_t = int(n_timesteps or self._n_timesteps)
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("TemporalUnet forward needs CUDA tensors: there is no CPU fallback in this implementation")
-        key = (int(horizon), device.index or 0, n_t, self.precision, tuple(sorted(self._diffusion_cfg.items())))
+        precision = precision or self.precision
+        key = (int(horizon), device.index or 0, n_t, precision, tuple(sorted(self._diffusion_cfg.items())))
         ent = self._engines.get(key)
         if ent is None:
-            eng = create_engine_auto(self.precision, transition_dim=self.transition_dim, dim=self.dim,
+            eng = create_engine_auto(precision, transition_dim=self.transition_dim, dim=self.dim,
                                      dim_mults=self.dim_mults, kernel_size=self.kernel_size, time_dim=self.time_dim,
                                      horizon=horizon, n_timesteps=n_t, max_batch=self.max_batch, device=device,
                                      **self._diffusion_cfg)
