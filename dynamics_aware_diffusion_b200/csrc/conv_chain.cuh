@@ -52,13 +52,20 @@ constexpr int CH_MAX_CONVS = DAD_CH_MAX_CONVS;
 constexpr int CH_MAX_NB = 8;          // weight-tile ring depth (runtime, <= 8)
 
 __host__ __device__ constexpr bool ch_narrow(int gw) { return gw == 16 || gw == 32; }
-// Epilogue shape per GroupNorm width (measured per layer in round 1): the narrow Conv1dBlocks are bound
-// by the epilogue's critical path and take 4 warpgroups x 8-column TMEM chunks; the MMA-bound wide layers 3 x 16;
-// width 256 pairs two warpgroups on the two halves of a group; width 128 (C_out = 1024, K >= 5120: an item's MMAs take
-// ~20 us, its two 128-column units ~8 us each) also runs two, which frees 32 KB of staging memory for the L = 4
-// bottleneck of the four-level U-Nets.
-__host__ __device__ constexpr int ch_nwg(int gw) { return gw >= 128 ? 2 : (ch_narrow(gw) ? 4 : 3); }
-__host__ __device__ constexpr int ch_cw(int gw) { return ch_narrow(gw) ? 8 : 16; }
+// Epilogue shape per GroupNorm width: 16-column TMEM chunks everywhere (8 independent fp32x2 chains per thread and loop
+// iteration: the epilogue is bound by dependent-instruction latency, not by a pipe; 8-column chunks were 2-8 % slower on
+// the narrow layers, 32-column chunks spill).  Warpgroups: 4 for the narrow Conv1dBlocks (widths 16 / 32: an L=32 item
+// is 4 units of work and TMEM holds only 2 such items), 3 for width 64 (MMA-bound), 2 for widths 128 / 256 (C_out >=
+// 1024, K >= 5120: an item's MMAs take ~20 us, its two 128-column units ~8 us each; two warpgroups also free 32 KB of
+// staging memory for the L = 4 bottleneck of the four-level U-Nets, and width 256 pairs them on the halves of a group).
+#ifndef DAD_CH_NARROW_NWG
+#define DAD_CH_NARROW_NWG 4
+#endif
+#ifndef DAD_CH_NARROW_CW
+#define DAD_CH_NARROW_CW 16
+#endif
+__host__ __device__ constexpr int ch_nwg(int gw) { return gw >= 128 ? 2 : (ch_narrow(gw) ? DAD_CH_NARROW_NWG : 3); }
+__host__ __device__ constexpr int ch_cw(int gw) { return ch_narrow(gw) ? DAD_CH_NARROW_CW : 16; }
 __host__ __device__ constexpr int ch_threads(int gw) { return 64 + 128 * ch_nwg(gw); }
 __host__ __device__ constexpr int ch_unit_cols(int gw) { return gw >= 128 ? 128 : 64; }
 __host__ __device__ constexpr int ch_stage_out_bytes(int gw) { return 128 * ch_unit_cols(gw) * 2; }
@@ -124,6 +131,13 @@ __host__ __device__ inline ChSmem ch_smem_layout(int a_stage_bytes, int n_a, int
   s.scratch = s.wparams + nwg * 2 * 20 * uc;                               // [warpgroup][2 buffers] x 20 B per column
   s.total = s.scratch + nwg * 2 * 4 * S_t * ch_groups_per_unit(gw) * 8 + 1024 /*alignment slack*/;
   return s;
+}
+
+template <int CW>
+__device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, uint32_t (&v)[32]) {
+  if constexpr (CW == 32) ptx::tmem_ld32(taddr, v);
+  else if constexpr (CW == 16) ptx::tmem_ld16(taddr, v);
+  else ptx::tmem_ld8(taddr, v);
 }
 
 template <int GW, int MH, int NS>
@@ -529,7 +543,7 @@ conv_chain_kernel(const __grid_constant__ ChainArgs args) {
 #pragma unroll
           for (int h = 0; h < MH; ++h) {
             uint32_t v[32];
-            if constexpr (CW == 16) ptx::tmem_ld16(t_addr_of(h) + col0 + c * CW, v); else ptx::tmem_ld8(t_addr_of(h) + col0 + c * CW, v);
+            tmem_ld_cw<CW>(t_addr_of(h) + col0 + c * CW, v);
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < CW / 2; ++j) {
@@ -580,7 +594,7 @@ conv_chain_kernel(const __grid_constant__ ChainArgs args) {
 #pragma unroll 1
         for (int c = 0; c < NCHUNK; ++c) {
           uint32_t v[32];
-          if constexpr (CW == 16) ptx::tmem_ld16(t_h + c * CW, v); else ptx::tmem_ld8(t_h + c * CW, v);
+          tmem_ld_cw<CW>(t_h + c * CW, v);
           const uint32_t sp = pb + (uint32_t)((c * CW) >> 1) * 32u;
           f32x2 y[CW / 2];
           if (!plain) {
