@@ -122,7 +122,7 @@ def stream_step_roofline(dev, pk, B=262144, H=32, T=6):
     in-kernel Philox, 805 MB with injected noise -- several times the 126 MB L2, so every byte comes from HBM."""
     import torch
     from dynamics_aware_diffusion_b200 import TemporalUnet, GaussianDiffusion, _native as N
-    net = TemporalUnet(T, dim=64, dim_mults=(1,), precision="fp32", max_batch=B)      # small arena; the U-Net is not run
+    net = TemporalUnet(T, dim=64, dim_mults=(1,), precision="bf16", max_batch=B)      # small arena; the U-Net is not run
     dif = GaussianDiffusion(net, horizon=H, observation_dim=T - 2, action_dim=2, n_timesteps=100).to(dev)
     eng = dif.engine(H, dev)
     eng.set_conditions({0: torch.zeros(1, T, device=dev)}, B)
@@ -135,6 +135,25 @@ def stream_step_roofline(dev, pk, B=262144, H=32, T=6):
         out[key] = {"achieved": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / pk["hbm"],
                     "avg_launch_ms": ms, "bytes_per_launch": nbytes}
     out["achieved"], out["frac"] = out["injected_noise"]["achieved"], out["injected_noise"]["frac"]
+    # The kernel the HEADLINE config runs -- step_project_fused_kernel, pointwise part + the D x D projector from shared
+    # memory -- at the same streaming size.  2*D*D = 73.7 kFLOP per 2.3 KB sample: 32 FLOP/B, three times the fp32-SIMT
+    # ridge of this machine, so at streaming sizes it is bound by the FMA pipe, not by HBM; reported as measured.
+    if H * T == WORKLOADS["pointmaze"]["H"] * (WORKLOADS["pointmaze"]["n"] + WORKLOADS["pointmaze"]["m"]):
+        pol, eng2, pflags, _, _ = attach_policy(dif, dict(WORKLOADS["pointmaze"], S=100), dev, B)
+        D = H * T
+        nbytes = 12 * D * B
+        fp = {}
+        # 0x400: the fused SIMT kernel (projector in shared memory); 0x200: pointwise kernel + bf16x3 tcgen05 GEMM (K8)
+        for key, extra, kern in (("fused_simt", 0x400, "step_project_fused_kernel"),
+                                 ("tensor_core", 0x200, "step_pointwise_kernel + conv_tc_kernel<128,0> (bf16x3 projector GEMM)")):
+            ms = eng2.time_step_kernel(B, 50, flags=pflags | extra, iters=10)
+            fp[key] = {"kernel": kern, "avg_launch_ms": ms, "achieved": nbytes / (ms * 1e-3) / 1e9,
+                       "frac": nbytes / (ms * 1e-3) / 1e9 / pk["hbm"], "projector_tflops": 2.0 * D * D * B / (ms * 1e-3) / 1e12}
+        fp["bytes_per_launch"] = nbytes
+        fp["note"] = ("algorithmic bytes 12*D per sample (read x, eps; write x); the projector adds 2*D*D FLOP per sample = "
+                      "%.0f FLOP/B: fp32-FMA-bound on SIMT, so large batches take the tensor-core path" % (2.0 * D * D / (12 * D)))
+        out["fused_projector"] = fp
+        del pol, eng2
     # DRAM bytes of one injected-noise launch at B=262144 (profiles/r01_ncu_full_stream_b262144.md)
     out["traffic"] = ncu_traffic("step_pointwise_kernel", "stream_b262144") if B == 262144 else None
     del eng, dif, net
@@ -142,11 +161,28 @@ def stream_step_roofline(dev, pk, B=262144, H=32, T=6):
     return out
 
 
+def workload_config(name, w, world, scaling):
+    """The `config` object of the JSON line: identical in both arms (b200 and reference) by construction."""
+    B_total = w["B"] if (scaling == "strong" or world == 1) else w["B"] * world
+    return {"workload": name, "description": w["label"], "B_total": B_total, "B_per_gpu": B_total // world, "H": w["H"],
+            "T": w["n"] + w["m"], "diffusion_steps": w["S"], "policy": "dynamics-aware" if w["dyn"] is not None else "guided",
+            "unet": "dim=%d mults=%s" % (w["dim"], ",".join(map(str, w["mults"]))),
+            "noise": "independent Gaussian per plan and step (GPU arm: in-kernel Philox; reference arm: torch.randn on the host)",
+            "parallelism": "batch sharded over the GPUs, replicated weights (reference arm: the host cores of one box, rank 0 only)",
+            "l2": "no flush: a diffusion step's working set (activations + weights, `working_set_mb` of the GPU arm's line) "
+                  "is produced and consumed inside the step and exceeds the 126 MB L2 from B=1024 per GPU up"}
+
+
 def run_reference(args, w, name):
-    """The reference's CPU sampler (its op sequence restated in torch, oracle/torch_port.py) on the host cores."""
+    """The reference's CPU sampler on the host cores.  With oracle/_ref staged (oracle/make_ref.py: the reference's own
+    files, byte for byte) the UNMODIFIED reference classes run -- `p_sample_with_guidance` -> `apply_projection` ->
+    `apply_conditions` per step, the composition the goldens pin (tests/golden/make_golden.py) -- and the line says
+    kind "reference"; otherwise the pinned restatement oracle/torch_port.py runs (kind "port")."""
+    import contextlib
+    import io
     import numpy as np
     import torch
-    from oracle import torch_port
+    from oracle import torch_port, ref_shim
     from dynamics_aware_diffusion_b200 import TemporalUnet, GaussianDiffusion, synthetic, projection_alphas
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -154,27 +190,58 @@ def run_reference(args, w, name):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     T = w["n"] + w["m"]
-    S = w["S"]
+    S, H = w["S"], w["H"]
     net = TemporalUnet(T, dim=w["dim"], dim_mults=w["mults"])
-    dif = GaussianDiffusion(net, horizon=w["H"], observation_dim=w["n"], action_dim=w["m"], n_timesteps=S)
+    dif = GaussianDiffusion(net, horizon=H, observation_dim=w["n"], action_dim=w["m"], n_timesteps=S)
     synthetic.fill_state_dict(dif, 0)
     sd = {k: v.detach() for k, v in dif.state_dict().items()}
     P, nz = projector_inputs(w)
-    projector = None
-    if P is not None:
-        al = projection_alphas(S, S, "noise_schedule", 1.0, sd["betas"])
-        projector = dict(P=P, alphas=[float(a) for a in al], n=w["n"], m=w["m"], H=w["H"],
-                         nz=tuple(torch.from_numpy(np.asarray(a, dtype=np.float32))
-                                  for a in (nz.obs_mean, nz.obs_std, nz.action_mean, nz.action_std)))
     Bc, dsteps = args.cpu_batch, args.cpu_diffusion_steps
     g = torch.Generator().manual_seed(1234)
     start = torch.zeros(T)
     start[:w["n"]] = torch.randn(w["n"], generator=g)
+    kind = "reference" if ref_shim.available() and not args.cpu_port else "port"
 
-    def one_sample():
-        x = torch.randn(Bc, w["H"], T, generator=g)
-        return torch_port.sample_loop(sd, x, lambda k: torch.randn(Bc, w["H"], T, generator=g), {0: start}, projector,
-                                      steps=dsteps)
+    if kind == "reference":
+        ref = ref_shim.load()
+        rnet = ref.TemporalUnet(T, dim=w["dim"], dim_mults=w["mults"])
+        rdif = ref.GaussianDiffusion(rnet, horizon=H, observation_dim=w["n"], action_dim=w["m"], n_timesteps=S)
+        rdif.load_state_dict(sd, strict=True)
+        rdif.eval()
+        with contextlib.redirect_stdout(io.StringIO()):
+            if P is not None:
+                rpol = ref.DynamicsAwarePolicy(rdif, projection_matrix=P, normalizer=nz, state_dim=w["n"],
+                                               observation_dim=w["n"], action_dim=w["m"], horizon=H,
+                                               projection_schedule="noise_schedule", projection_strength=1.0)
+            else:
+                rpol = ref.GuidedPolicy(rdif, nz)
+        cond = {0: start[None]}
+
+        @torch.no_grad()
+        def one_sample():
+            # torch.randn inside p_sample_with_guidance draws the step noise, as in the reference
+            x = rpol.apply_conditions(torch.randn(Bc, H, T, generator=g), cond)
+            for i in reversed(range(S - dsteps, S)):
+                t = torch.full((Bc,), i, dtype=torch.long)
+                if P is not None:          # denoise -> project -> inpaint (README.md:24-25)
+                    x = rpol.p_sample_with_guidance(x, t, None)
+                    x = rpol.apply_projection(x, i)
+                    x = rpol.apply_conditions(x, cond)
+                else:
+                    x = rpol.p_sample_with_guidance(x, t, cond)
+            return x
+    else:
+        projector = None
+        if P is not None:
+            al = projection_alphas(S, S, "noise_schedule", 1.0, sd["betas"])
+            projector = dict(P=P, alphas=[float(a) for a in al], n=w["n"], m=w["m"], H=H,
+                             nz=tuple(torch.from_numpy(np.asarray(a, dtype=np.float32))
+                                      for a in (nz.obs_mean, nz.obs_std, nz.action_mean, nz.action_std)))
+
+        def one_sample():
+            x = torch.randn(Bc, H, T, generator=g)
+            return torch_port.sample_loop(sd, x, lambda k: torch.randn(Bc, H, T, generator=g), {0: start}, projector,
+                                          steps=dsteps)
 
     for _ in range(args.warmup):
         one_sample()
@@ -188,12 +255,12 @@ def run_reference(args, w, name):
     line = {
         "impl": "reference", "metric": "plans/sec", "value": value, "unit": "plans/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "description": w["label"], "B_per_gpu": w["B"], "H": w["H"], "T": T,
-                   "diffusion_steps": S, "policy": "dynamics-aware" if P is not None else "guided",
-                   "unet": "dim=%d mults=%s" % (w["dim"], ",".join(map(str, w["mults"]))),
-                   "noise": "torch.randn on the host", "parallelism": "host cores of one box (rank 0 only)"},
-        "cpu_baseline": {"value": value, "unit": "plans/s", "cores": cores, "kind": "port", "sample": sample,
+        "scaling": "weak" if (args.gpus > 1 and args.scaling == "weak") else "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(name, w, args.gpus, args.scaling),
+        "cpu_baseline": {"value": value, "unit": "plans/s", "cores": cores, "kind": kind, "sample": sample,
+                         "code": ("the reference's own modules (oracle/_ref, staged by oracle/make_ref.py)" if kind == "reference"
+                                  else "oracle/torch_port.py (restatement pinned to the reference by tests/golden)"),
                          "ms_per_diffusion_step_at_sample_B": per_dstep * 1e3},
         "e2e": {"value": value, "unit": "plans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -332,6 +399,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=256)
     ap.add_argument("--cpu-diffusion-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-port", action="store_true", help="reference arm: time oracle/torch_port.py even when oracle/_ref is staged")
     ap.add_argument("--no-extra-legs", action="store_true", help="skip the other BASELINE configs, the sweep and the eager-PyTorch comparator")
     ap.add_argument("--layers-out", default="", help="write the per-layer / per-launch timing tables (JSON) to this file")
     args = ap.parse_args()
@@ -478,12 +546,8 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak" if (world > 1 and args.scaling == "weak") else "strong",
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "description": w["label"], "B_total": B_total, "B_per_gpu": B, "H": H, "T": T,
-                   "diffusion_steps": S, "policy": "dynamics-aware" if dyn else "guided",
-                   "unet": "dim=%d mults=%s" % (w["dim"], ",".join(map(str, w["mults"]))),
-                   "noise": "in-kernel Philox", "parallelism": "batch-sharded x%d, replicated weights" % world,
-                   "l2": "working set per diffusion step (%.0f MB of activations + weights at B=%d) exceeds the 126 MB L2; no flush"
-                         % (info["workspace_bytes"] / 1e6 * B / max(w["B"], 1), B)},
+        "config": workload_config(args.workload, w, world, args.scaling),
+        "working_set_mb": round(info["workspace_bytes"] / 1e6 * B / max(w["B"], 1), 1),
         "e2e": {"value": e2e_value, "unit": "plans/s", "h2d_bytes_per_step": bytes_io, "d2h_bytes_per_step": bytes_io},
         "gpu_launches": int(launches), "launches_per_diffusion_step": info["launches_per_step"], "clocks": clocks,
     }

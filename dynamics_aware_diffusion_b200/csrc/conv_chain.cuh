@@ -161,6 +161,7 @@ conv_chain_kernel(const __grid_constant__ ChainArgs args) {
   constexpr int GPC = (GW < CW) ? CW / GW : 1;            // groups per column chunk
   constexpr int CPG = (GW >= CW) ? (XWG ? NCHUNK : GW / CW) : 1;   // chunks of a unit that make up one (partial) group
   constexpr int PBUF = 20 * UC;                           // bytes of one per-unit parameter buffer
+  constexpr bool SPLIT8 = ch_narrow(GW) && CW == 16;      // pass 1 keeps conv_t3's 8-column summation order
   static_assert(!XWG || (NWG == 2 && UPI == 2), "cross-warpgroup statistics: one warpgroup per half of the item");
   constexpr uint16_t MC_MASK = 3;
 
@@ -532,6 +533,10 @@ conv_chain_kernel(const __grid_constant__ ChainArgs args) {
           f32x2 s1[GPC], s2[GPC];
 #pragma unroll
           for (int g = 0; g < GPC; ++g) { s1[g] = pk2(0.f, 0.f); s2[g] = pk2(0.f, 0.f); }
+          // narrow layers: the sums of columns 8..15 of the chunk are kept apart and added afterwards, which is the
+          // association order of the 8-column chunks of conv_t3.cuh -- the two kernel families stay bit-identical
+          // (tests/test_gpu_chain.py::test_fusion_levels_bit_identical)
+          f32x2 u1 = pk2(0.f, 0.f), u2 = pk2(0.f, 0.f);
           const uint32_t sb = pb_bias + (uint32_t)(c * CW) * 4u;
           f32x2 bb[CW / 2];
 #pragma unroll
@@ -549,13 +554,22 @@ conv_chain_kernel(const __grid_constant__ ChainArgs args) {
             for (int j = 0; j < CW / 2; ++j) {
               const f32x2 x = fadd2(pk2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bb[j]);
               const int g = (GW < CW) ? (2 * j) / GW : 0;       // compile-time (GW is even)
-              s1[g] = fadd2(s1[g], x);
-              s2[g] = ffma2(x, x, s2[g]);
+              if (SPLIT8 && j >= 4) {
+                u1 = fadd2(u1, x);
+                u2 = ffma2(x, x, u2);
+              } else {
+                s1[g] = fadd2(s1[g], x);
+                s2[g] = ffma2(x, x, s2[g]);
+              }
             }
           }
           if constexpr (GW >= CW) {
             run1 = fadd2(run1, s1[0]);
             run2 = fadd2(run2, s2[0]);
+            if constexpr (SPLIT8) {
+              run1 = fadd2(run1, u1);
+              run2 = fadd2(run2, u2);
+            }
             if ((c + 1) % CPG != 0) continue;
             s1[0] = run1; s2[0] = run2;
             run1 = pk2(0.f, 0.f); run2 = pk2(0.f, 0.f);

@@ -16,6 +16,12 @@
 // shared memory as a 128 x 64 K-major tile with the 128-byte swizzle tcgen05 expects.
 // B operand: pre-packed bf16 weights Wb[n][tap * Cin + c] (K-major), 2-D TMA, same swizzle.
 //
+// Weight-stationary mode (p.ws, chosen by the host when K x BN weights + the activation ring fit shared memory: the
+// Downsample / ConvTranspose convs of the narrow levels): a persistent CTA always works on the same N tile (the grid is a
+// multiple of n_tiles_n), so its weight boxes are fetched ONCE -- before griddepcontrol.wait, they are constants -- and
+// only activation boxes stream through the ring.  Without it every M tile re-fetched the whole weight tile: L2->SM
+// traffic was 3-6x the DRAM traffic (profiles/r01_ncu_full_pointmaze.md) and bounded these kernels.
+//
 // Warp roles (320 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = TMEM allocator +
 // single-thread MMA issuer, warps 2-9 = two epilogue warpgroups (TMEM -> registers -> global) that take
 // alternate tiles.  Up to four TMEM accumulator stages let the MMAs run ahead of the epilogues.
@@ -58,6 +64,7 @@ struct ConvTcParams {
   const float *alpha_tab;
   const float *cond_vals;
   int T;
+  int ws;                        // 1: weight-stationary (the CTA's whole weight tile stays in shared memory, see below)
   unsigned long long *prof;      // optional cycle counters (DAD_TC_PROF): [wait, pass1, pass2, tiles] summed over epilogue warps
   int debug;                     // 0 normal; 1 = skip the epilogue arithmetic; 2 = skip TMA + MMA (profiling only, DAD_TC_DEBUG)
 };
@@ -75,6 +82,11 @@ struct TcCfg {
   static constexpr int BAR_BYTES = 256;
   // + per-column epilogue parameters (bias, gamma, beta, time bias) for every output channel: 16 B per channel
   static constexpr int smem_bytes(int cout_pad) { return STAGES * STAGE_BYTES + 1024 /*align slack*/ + BAR_BYTES + 16 * cout_pad; }
+  // Weight-stationary layout: the ring holds activation boxes only, the num_kb weight boxes of the CTA's N tile follow it.
+  __host__ __device__ static constexpr int ring_bytes(bool ws, int num_kb) { return ws ? STAGES * A_BYTES + num_kb * B_ALLOC : STAGES * STAGE_BYTES; }
+  static constexpr int smem_bytes_ws(int cout_pad, int num_kb) {
+    return ring_bytes(true, num_kb) + 1024 + BAR_BYTES + 16 * cout_pad;
+  }
 };
 
 // tanh(softplus(y)) = (w - 1) / (w + 1) with w = (1 + e^y)^2, i.e. 1 - 2 / (w + 1): one ex2, one rcp, no clamp
@@ -100,20 +112,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  const int kch = p.kch1 + p.kch2;
+  const int num_kb = p.taps * kch;
+  const bool ws = p.ws != 0;
+  const int ring_bytes = Cfg::ring_bytes(ws, num_kb);
+  const int a_stride = ws ? Cfg::A_BYTES : Cfg::STAGE_BYTES;     // distance between activation slots of the ring
+  uint8_t *w_res = smem + Cfg::STAGES * Cfg::A_BYTES;            // resident weight boxes (ws only)
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + ring_bytes);
   uint64_t *empty_bar = full_bar + Cfg::STAGES;
   uint64_t *tfull_bar = empty_bar + Cfg::STAGES;
   uint64_t *tempty_bar = tfull_bar + Cfg::ACC_STAGES;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + Cfg::ACC_STAGES);
+  uint64_t *wfull_bar = tempty_bar + Cfg::ACC_STAGES;            // resident weights have landed (ws only)
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(wfull_bar + 1);
   const int cout_pad = p.n_tiles_n * BN;
   // per-column epilogue parameters, interleaved: s_par[col] = {gamma, beta, bias, time bias} (one LDS.128 per column)
-  const uint32_t s_par = ptx::smem_u32(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
+  const uint32_t s_par = ptx::smem_u32(smem + ring_bytes + Cfg::BAR_BYTES);
   __shared__ float gn_scratch[TC_EPI_WG][4][2 * 8];   // [warpgroup][epilogue warp][sum, sumsq per group]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.n_tiles_m * p.n_tiles_n;
-  const int kch = p.kch1 + p.kch2;
-  const int num_kb = p.taps * kch;
   const int spt = TC_BM / p.L_out;              // samples per M-tile
 
   ptx::griddep_launch();
@@ -129,7 +146,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       ptx::mbar_init(&tfull_bar[s], 1);
       ptx::mbar_init(&tempty_bar[s], 4);        // one arrive per warp of the warpgroup that drained it
     }
+    ptx::mbar_init(wfull_bar, 1);
     ptx::fence_barrier_init();
+    if (ws && (int)blockIdx.x < total_tiles) {
+      // the weights are constants: fetch this CTA's whole N tile now, while the previous kernel is still running
+      const int n0 = ((int)blockIdx.x % p.n_tiles_n) * BN;
+      ptx::mbar_arrive_expect_tx(wfull_bar, (uint32_t)num_kb * Cfg::B_BYTES);
+      for (int kb = 0; kb < num_kb; ++kb) ptx::tma_load_2d(w_res + kb * Cfg::B_ALLOC, &tmW, wfull_bar, kb * TC_BK, n0);
+    }
   }
   if (warp == 1) {
     ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -168,12 +192,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         for (int kb = 0; kb < num_kb; ++kb) {
           const int tap = kb / kch, ch = kb - tap * kch;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t *sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t *sa = smem + stage * a_stride;
           uint8_t *sb = sa + Cfg::A_BYTES;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], ws ? Cfg::A_BYTES : Cfg::A_BYTES + Cfg::B_BYTES);
           if (ch < p.kch1) ptx::tma_load_4d(sa, &tmA1, &full_bar[stage], ch * TC_BK, p.tap_p[tap], p.tap_j[tap], b0);
           else ptx::tma_load_4d(sa, &tmA2, &full_bar[stage], (ch - p.kch1) * TC_BK, p.tap_p[tap], p.tap_j[tap], b0);
-          ptx::tma_load_2d(sb, &tmW, &full_bar[stage], kb * TC_BK, n0);
+          if (!ws) ptx::tma_load_2d(sb, &tmW, &full_bar[stage], kb * TC_BK, n0);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -186,6 +210,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      if (ws && (int)blockIdx.x < total_tiles) ptx::mbar_wait(wfull_bar, 0);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int as = it % Cfg::ACC_STAGES;
         const uint32_t aphase = (it / Cfg::ACC_STAGES) & 1;
@@ -195,9 +220,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         for (int kb = 0; kb < ((DAD_DEBUG_BITS(p) & 2) ? 0 : num_kb); ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);      // TMA bytes have landed
           ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sa = ptx::smem_u32(smem + stage * a_stride);
           const uint64_t da = ptx::make_smem_desc_sw128(sa);
-          const uint64_t db = ptx::make_smem_desc_sw128(sa + Cfg::A_BYTES);
+          const uint64_t db = ptx::make_smem_desc_sw128(ws ? ptx::smem_u32(w_res + kb * Cfg::B_ALLOC) : sa + Cfg::A_BYTES);
 #pragma unroll
           for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
             // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in 16 B units

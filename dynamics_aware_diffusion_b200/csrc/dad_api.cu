@@ -109,6 +109,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 
 }  // namespace
 
+// Batch from which the dynamics projector runs on the tensor cores even though the fused SIMT kernel fits (D*D*4 B in
+// shared memory).  INT_MAX = never; set from the measured cross-over.
+constexpr int kProjTcMinBatch = INT_MAX;
+
 struct dad_handle {
   dad_config cfg{};
   std::string err;
@@ -141,6 +145,11 @@ struct dad_handle {
   int projKp = 0, projNp = 0;
   CUtensorMap tmProjA, tmProjW;
   bool proj_tc = false;
+  // The fused SIMT projector (projector in shared memory) wins while the batch is small enough to be latency-bound; from
+  // this batch on the tensor-core path (pointwise + bf16x3 GEMM) is used even when the fused kernel fits (measured
+  // cross-over, tools/step_times.py).  force_proj_tc: measurement switch of dad_time_step_kernel (flag 0x200).
+  int proj_tc_min_batch = kProjTcMinBatch;
+  bool force_proj_tc = false;
   // conditions
   int n_cond = 0, cond_per_batch = 0, cond_B = 0;
   int cond_h[kMaxCond] = {0};
@@ -882,7 +891,9 @@ int enqueue_chain(dad_handle *h, ChainUnit &cu, int B, cudaStream_t st, int flag
 template <int BN, int GW>
 int launch_tc(dad_handle *h, const ConvOp &op, const ConvTcParams &p, int grid, cudaStream_t st) {
   auto kern = conv_tc_kernel<BN, GW>;
-  launch_k(kern, dim3((unsigned)grid), dim3(TC_THREADS), (size_t)TcCfg<BN>::smem_bytes(op.Cout_pad), st, 1, op.tmA1, op.tmA2, op.tmW, p);
+  const int num_kb = p.taps * (p.kch1 + p.kch2);
+  const size_t smem = p.ws ? (size_t)TcCfg<BN>::smem_bytes_ws(op.Cout_pad, num_kb) : (size_t)TcCfg<BN>::smem_bytes(op.Cout_pad);
+  launch_k(kern, dim3((unsigned)grid), dim3(TC_THREADS), smem, st, 1, op.tmA1, op.tmA2, op.tmW, p);
   return DAD_OK;
 }
 
@@ -1006,7 +1017,17 @@ int enqueue_tc(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
   p.B = B;
   p.n_tiles_m = cdiv((long long)B * op.g.L_out, TC_BM);
   const int tiles = p.n_tiles_m * p.n_tiles_n;
-  const int grid = std::min(tiles, h->sm_count);
+  int grid = std::min(tiles, h->sm_count);
+  // Weight-stationary (conv_tc.cuh): when the whole K x 128 weight tile fits beside the activation ring and every CTA
+  // sees several M tiles, keep it resident.  Needs a fixed N tile per CTA: a grid that is a multiple of n_tiles_n.
+  {
+    const int num_kb = p.taps * (p.kch1 + p.kch2);
+    const int g_ws = std::min(tiles, h->sm_count / p.n_tiles_n * p.n_tiles_n);
+    // 2 KB of static shared memory (GroupNorm scratch) also counts against the opt-in limit
+    p.ws = (op.BN == 128 && tuning_env("DAD_TC_WS", 1) != 0 && g_ws > 0 && tiles >= 2 * g_ws &&
+            TcCfg<128>::smem_bytes_ws(op.Cout_pad, num_kb) + 2048 <= h->max_smem_optin) ? 1 : 0;
+    if (p.ws) grid = g_ws;
+  }
   int rc = DAD_ERR_INVALID;
 #define TC_CASE(bn, gw) if (op.BN == bn && op.GW == gw) rc = launch_tc<bn, gw>(h, op, p, grid, st);
   TC_CASE(64, 8) TC_CASE(128, 16) TC_CASE(128, 32) TC_CASE(128, 64) TC_CASE(128, 128) TC_CASE(256, 256)
@@ -1161,7 +1182,7 @@ int enqueue_step(dad_handle *h, const float *model_out, int B, bool project, boo
     const int grid = (int)std::min<size_t>(cdiv(total4, 256), (size_t)h->sm_count * h->step_ctas_per_sm);
     launch_k(step_pointwise_kernel, dim3(grid), dim3(256), 0, st, 1, p);
     h->counting += 1;
-  } else if (h->proj_tc && !step_fused_fits(h)) {
+  } else if (h->proj_tc && (!step_fused_fits(h) || B >= h->proj_tc_min_batch || h->force_proj_tc)) {
     // large D (the projector does not fit shared memory): pointwise part -> x' (fp32) + its bf16 (hi | lo | hi) split; then one tcgen05 GEMM against (N_hi | N_hi | N_lo)
     // whose epilogue blends, inpaints and writes x (K8)
     p.to_tmp = 1;
@@ -1257,17 +1278,25 @@ void drop_graphs(dad_handle *h) {
   h->graphs.clear();
 }
 
-int get_graph(dad_handle *h, int B, bool project, GraphEntry **out) {
-  const long long key = (long long)B * 2 + (project ? 1 : 0);
+// One captured graph = `reps` consecutive diffusion steps (each: [stage x, step index -= 1] -> U-Net -> fused step
+// kernel).  Several steps per graph keep the programmatic (PDL) edges ACROSS step boundaries and cut the number of
+// graph launches per plan (500 -> 25 for the B = 1 plan of get_action).
+constexpr int kStepsPerGraph = 20;
+
+int get_graph(dad_handle *h, int B, bool project, int reps, GraphEntry **out) {
+  const long long key = ((long long)B * 2 + (project ? 1 : 0)) * 64 + reps;
   auto it = h->graphs.find(key);
   if (it != h->graphs.end()) { *out = &it->second; return DAD_OK; }
   cudaGraph_t graph = nullptr;
   h->counting = 0;
   CK(h, cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
-  // captured step: [stage x, step index -= 1] -> U-Net -> fused step kernel; the loop starts one index high
+  // the loop starts one index high: every captured step first decrements it
   const bool fork = tuning_env("DAD_FORK", 1) != 0;
-  int rc = enqueue_unet(h, B, h->cap_stream, true, fork ? h->side_stream : nullptr);
-  if (!rc) rc = enqueue_step(h, h->d_eps, B, project, false, h->cap_stream);
+  int rc = DAD_OK;
+  for (int r = 0; r < reps && !rc; ++r) {
+    rc = enqueue_unet(h, B, h->cap_stream, true, fork ? h->side_stream : nullptr);
+    if (!rc) rc = enqueue_step(h, h->d_eps, B, project, false, h->cap_stream);
+  }
   cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
   if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
   if (e != cudaSuccess) DAD_FAIL(h, DAD_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
@@ -1795,10 +1824,17 @@ int dad_sample(dad_handle *h, float *x, const float *noise_seq, uint64_t seed, u
       init_x_kernel<<<cdiv((size_t)Bc * D / 4, 256), 256, 0, st>>>(h->d_ls, h->d_cond, Bc, (int)D, h->cfg.transition_dim, draw ? 1 : 0);
       h->launches += 1;
     }
-    GraphEntry *ge = nullptr;
-    if ((rc = get_graph(h, Bc, project, &ge))) return rc;
-    for (int s = 0; s < n_steps; ++s) CK(h, cudaGraphLaunch(ge->exec, st));
-    h->launches += ge->kernels * n_steps;
+    // whole multiples of kStepsPerGraph through the multi-step graph, the remainder step by step
+    const int reps = std::min(n_steps, kStepsPerGraph);
+    GraphEntry *ge = nullptr, *ge1 = nullptr;
+    if ((rc = get_graph(h, Bc, project, reps, &ge))) return rc;
+    int done = 0;
+    for (; done + reps <= n_steps; done += reps) CK(h, cudaGraphLaunch(ge->exec, st));
+    h->launches += ge->kernels * (done / reps);
+    if (done < n_steps) {
+      if ((rc = get_graph(h, Bc, project, 1, &ge1))) return rc;
+      for (; done < n_steps; ++done) { CK(h, cudaGraphLaunch(ge1->exec, st)); h->launches += ge1->kernels; }
+    }
   }
   return DAD_OK;
 }
@@ -2038,7 +2074,7 @@ int dad_sample_profile(dad_handle *h, float *x, uint64_t seed, uint64_t sample_o
     h->launches += 1;
   }
   GraphEntry *ge = nullptr;
-  if ((rc = get_graph(h, B, project, &ge))) return rc;
+  if ((rc = get_graph(h, B, project, 1, &ge))) return rc;
   std::vector<cudaEvent_t> ev(n_steps + 1);
   for (auto &e : ev) CK(h, cudaEventCreate(&e));
   CK(h, cudaEventRecord(ev[0], st));
@@ -2213,7 +2249,11 @@ int dad_time_step_kernel(dad_handle *h, int32_t B, int32_t step, uint32_t flags,
   }
   CK(h, cudaMemsetAsync(h->d_hostx, 0, n * sizeof(float), st));
   const bool injected = (flags & 0x100u) != 0;      // measurement only: read the noise from a buffer instead of Philox
-  flags &= ~0x100u;
+  h->force_proj_tc = (flags & 0x200u) != 0;         // measurement only: projector on the tensor cores whatever the batch
+  const bool fused_simt = (flags & 0x400u) != 0;    // measurement only: the fused SIMT projector whatever the batch
+  flags &= ~0x700u;
+  const int saved_min_batch = h->proj_tc_min_batch;
+  if (fused_simt) h->proj_tc_min_batch = INT_MAX;
   if (injected) {
     if (n > h->hostnoise_cap) {
       int rc;
@@ -2236,6 +2276,8 @@ int dad_time_step_kernel(dad_handle *h, int32_t B, int32_t step, uint32_t flags,
   h->counting = 0;
   rc = time_launches(h, st, iters, ms, [&]() { return enqueue_step(h, h->d_eps, B, project, false, st); });
   h->launches += h->counting;
+  h->force_proj_tc = false;
+  h->proj_tc_min_batch = saved_min_batch;
   return rc;
 }
 

@@ -30,6 +30,16 @@ def extract(a: torch.Tensor, t: torch.Tensor, x_shape: tuple) -> torch.Tensor:
     return a.gather(-1, t).reshape(t.shape[0], *((1,) * (len(x_shape) - 1)))
 
 
+def uniform_timestep(t: torch.Tensor) -> int:
+    """The step index shared by the whole batch, with ONE device read (min and max together).  The fused step kernel
+    takes one index per call, which is how every loop of the reference calls p_sample (diffusion.py:247-249,
+    policies.py:141-143)."""
+    lo, hi = torch.stack(torch.aminmax(t.reshape(-1))).tolist()
+    if lo != hi:
+        raise NotImplementedError("p_sample with per-row timesteps: the fused step kernel takes one step index")
+    return int(lo)
+
+
 def _derived_buffers(betas):
     one = 1.0
     alphas = one - betas
@@ -156,11 +166,9 @@ class GaussianDiffusion(nn.Module):
     @torch.no_grad()
     def p_sample(self, x, t):
         """x_{t-1} ~ p(.|x_t) (diffusion.py:205-223): native U-Net + fused step kernel; noise = torch.randn_like."""
-        step = int(t.reshape(-1)[0])
+        step = uniform_timestep(t)
         eng = self.engine(x.shape[1], x.device)
         xc = x.contiguous().float()
-        if not bool((t == step).all()):
-            raise NotImplementedError("p_sample with per-row timesteps: the fused step kernel takes one step index")
         eps = eng.unet_forward(xc, step=step)
         noise = torch.randn_like(x)
         out = xc.clone()

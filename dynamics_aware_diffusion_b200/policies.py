@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 
 from . import _native as N
-from .diffusion import _run_loop
+from .diffusion import _run_loop, uniform_timestep
 from .projection import fold_projection, projection_alphas
 
 
@@ -51,6 +51,7 @@ class GuidedPolicy(nn.Module):
         self.capture_guidance = os.environ.get("DAD_GUIDED_GRAPH", "1") != "0"
         self._guided_graphs = {}
         self._capture_error = None
+        self._pin_cond = self._pin_plan = None
 
     # ---- hooks overridden by DynamicsAwarePolicy --------------------------------------------------
     def _loop_flags(self, engine):
@@ -78,7 +79,7 @@ class GuidedPolicy(nn.Module):
     @torch.no_grad()
     def p_sample_with_guidance(self, x, t, conditions=None):
         """One guided, conditioned reverse step (policies.py:65-112)."""
-        step = int(t.reshape(-1)[0])
+        step = uniform_timestep(t)
         eng = self._engine(x.device)
         xc = x.contiguous().float()
         eps = eng.unet_forward(xc, step=step)
@@ -246,10 +247,18 @@ class GuidedPolicy(nn.Module):
             return self.action_buffer.pop(0)
         device = self.diffusion.betas.device
         obs = self.normalizer.normalize_observations(self._process_observation(observation))
-        start = torch.zeros(1, self.transition_dim, device=device)
-        start[:, :self.observation_dim] = torch.as_tensor(np.asarray(obs), dtype=torch.float32, device=device)
+        # the condition goes up and the plan comes down through PINNED staging buffers (allocated once): no pageable
+        # bounce copies on the per-replan path
+        if self._pin_cond is None or self._pin_cond.shape[1] != self.transition_dim:
+            self._pin_cond = torch.zeros(1, self.transition_dim).pin_memory()
+            self._pin_plan = torch.empty(self.horizon, self.transition_dim).pin_memory()
+        self._pin_cond.zero_()
+        self._pin_cond[0, :self.observation_dim] = torch.as_tensor(np.asarray(obs), dtype=torch.float32).reshape(-1)
+        start = self._pin_cond.to(device, non_blocking=True)
         plan = self.sample_loop(batch_size=1, conditions={0: start}, verbose=False)
-        self._fill_action_buffer(plan)
+        self._pin_plan.copy_(plan[0], non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+        self._fill_action_buffer(self._pin_plan[None])
         return self.action_buffer.pop(0)
 
 

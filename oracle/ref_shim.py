@@ -4,15 +4,31 @@ The reference's package __init__ imports a module that is not in its tree
 (m_diffuser/__init__.py:12 -> m_diffuser.datasets) and its dynamics package
 pulls gymnasium/minari (m_diffuser/dynamics/__init__.py:2-4).  We pre-seed empty
 package objects whose __path__ points into /root/reference so that the hot-path
-modules import normally.  Only `tests/golden/make_golden.py` and the optional
-`-m "not gpu"` live-reference tests use this; it is never available on the GPU
-box (no /root/reference there) and nothing in the product imports it.
+modules import normally.  Users: `tests/golden/make_golden.py`, the optional
+`-m "not gpu"` live-reference tests, and bench.py's reference arm / cpu_baseline
+leg.  Root: $DAD_REFERENCE_ROOT, else /root/reference (this container), else
+oracle/_ref (the byte-for-byte staging of the path's files made by
+oracle/make_ref.py, git-ignored, which is what exists on the GPU box).  Nothing
+in the product imports it.
 """
 import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("DAD_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _root():
+    env = os.environ.get("DAD_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", _STAGED):
+        if os.path.isdir(os.path.join(cand, "m_diffuser", "models")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _root()
 
 
 def available() -> bool:

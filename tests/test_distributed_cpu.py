@@ -32,11 +32,25 @@ def _worker(rank, world, port, total, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        lin = torch.nn.Linear(3, 2)
+        class Net(torch.nn.Module):
+            """float parameters + an integer buffer (two packed buffers), and the re-pack hook of TemporalUnet"""
+
+            def __init__(self):
+                super().__init__()
+                self.lin = torch.nn.Linear(3, 2)
+                self.register_buffer("steps", torch.full((5,), rank + 7, dtype=torch.long))
+                self.invalidated = 0
+
+            def invalidate(self):
+                self.invalidated += 1
+
+        lin = Net()
         with torch.no_grad():
-            lin.weight.fill_(float(rank + 1))
+            lin.lin.weight.fill_(float(rank + 1))
+            lin.lin.bias.fill_(float(10 * (rank + 1)))
         broadcast_module(lin, src=0)
-        ok_bcast = bool((lin.weight == 1.0).all())
+        ok_bcast = (bool((lin.lin.weight == 1.0).all()) and bool((lin.lin.bias == 10.0).all())
+                    and bool((lin.steps == 7).all()) and lin.invalidated == 1)
 
         def sample_fn(batch_size, conditions, sample_offset, **kw):
             # a stand-in sampler: row value = global row index, plus the per-row condition

@@ -11,7 +11,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KEYS = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+KEYS = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__grid_size",
@@ -25,9 +25,14 @@ KEYS = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "lts__t_bytes.sum", "sm__warps_active.avg.pct_of_peak_sustained_active"]
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
+# --out DIR: write there instead of profiles/ (on the GPU box only gpurun_out/ travels back)
+OUT = os.path.join(ROOT, "profiles")
+if sys.argv[1] == "--out":
+    OUT = sys.argv[2]
+    del sys.argv[1:3]
 tag, workload = sys.argv[1], sys.argv[2]
 pairs = list(zip(sys.argv[3::2], sys.argv[4::2]))
-traffic_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+traffic_path = os.path.join(OUT, "ncu_traffic.json")
 traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
 out = ["# ncu --set full --clock-control none, %s, workload %s\n" % (tag, workload)]
 for label, rep in pairs:
@@ -50,6 +55,6 @@ for label, rep in pairs:
         best = max(tot)
         traffic.setdefault(workload, {})[label] = best[1]
         out.append("DRAM traffic (read + write) of the longest of the %d captured launches: %.1f MB\n" % (len(tot), best[1] / 1e6))
-open(os.path.join(ROOT, "profiles", "%s_ncu_full_%s.md" % (tag, workload)), "w").write("\n".join(out))
+open(os.path.join(OUT, "%s_ncu_full_%s.md" % (tag, workload)), "w").write("\n".join(out))
 json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
 print("\n".join(out)[:2500])
