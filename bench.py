@@ -124,6 +124,7 @@ def stream_step_roofline(dev, pk, B=262144, H=32, T=6):
     from dynamics_aware_diffusion_b200 import TemporalUnet, GaussianDiffusion, _native as N
     net = TemporalUnet(T, dim=64, dim_mults=(1,), precision="bf16", max_batch=B)      # small arena; the U-Net is not run
     dif = GaussianDiffusion(net, horizon=H, observation_dim=T - 2, action_dim=2, n_timesteps=100).to(dev)
+    dif.fp32_ill_conditioned_steps = False      # only the step kernels run here: no fp32 sibling (and its arena) needed
     eng = dif.engine(H, dev)
     eng.set_conditions({0: torch.zeros(1, T, device=dev)}, B)
     out = {"bound": "hbm", "peak": pk["hbm"], "unit": "GB/s", "kernel": "step_pointwise_kernel",
@@ -334,6 +335,40 @@ def config_leg(name, dev, pk, overrides, dsteps=10):
     torch.cuda.empty_cache()
     out["setup_s"] = round(time.perf_counter() - t0, 1)
     return out
+
+
+def sharded_leg(name, dev, pk, world, dist, B_total, dsteps=10):
+    """BASELINE.json configs 3 / 4 on N GPUs (every rank calls this): the batch B_total split evenly over the ranks, each
+    rank times `dsteps` diffusion steps of its shard (config_leg), the step latency is the MAX over ranks, and the final
+    trajectory all-gather (C2) is timed on its own and added once per plan."""
+    import torch
+    w = WORKLOADS[name]
+    Bg = B_total // world
+    out = config_leg(name, dev, pk, {"B": Bg, "max_batch": Bg}, dsteps)
+    t = torch.tensor([out["p50_step_latency_ms"]], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    p50 = float(t.item())
+    T = w["n"] + w["m"]
+    x = torch.zeros(Bg, w["H"], T, device=dev)
+    g = torch.empty(Bg * world, w["H"], T, device=dev)
+    dist.all_gather_into_tensor(g, x)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        dist.all_gather_into_tensor(g, x)
+    e1.record()
+    torch.cuda.synchronize()
+    gt = torch.tensor([e0.elapsed_time(e1) / 3], device=dev, dtype=torch.float64)
+    dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+    S = w["S"]
+    plan_ms = p50 * S + float(gt.item())
+    return {"workload": name, "n_gpus": world, "B_total": Bg * world, "B_per_gpu": Bg, "H": w["H"], "T": T,
+            "diffusion_steps": S, "unet": out["unet"], "policy": out["policy"], "timed_diffusion_steps": dsteps,
+            "p50_step_latency_ms_max_over_ranks": p50, "gather_ms": float(gt.item()),
+            "plans_per_s_extrapolated": Bg * world / (plan_ms * 1e-3),
+            "unet_tensor_frac_of_sustained_per_gpu": out["unet_tensor_frac_of_sustained"] * out["p50_step_latency_ms"] / p50}
 
 
 def gpu_eager_baseline(w, dev, B, dsteps=3):
@@ -555,6 +590,17 @@ def main():
         line["nccl_check"] = nccl_check
     if other:
         line["other_scaling"] = other
+
+    # ---- BASELINE.json configs 3 and 4 on N GPUs: HalfCheetah B = 1024 per GPU (8192 over 8), Door B = 4096 split N ways
+    if world > 1 and not args.no_extra_legs:
+        pk_all = peaks()
+        multi = []
+        for name, bt in (("halfcheetah", WORKLOADS["halfcheetah"]["B"] * world), ("door", WORKLOADS["door"]["B"])):
+            try:
+                multi.append(sharded_leg(name, dev, pk_all, world, dist, bt))
+            except Exception as exc:      # a failing extra must not take the headline line with it (all ranks fail alike)
+                multi.append({"workload": name, "error": str(exc)[:300]})
+        line["configs_multi_gpu"] = multi
 
     if rank == 0:
         pk = peaks()

@@ -255,6 +255,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     constexpr int CPG = (GW >= CW) ? GW / CW : 1;              // column chunks per GroupNorm group
     int it = wg;
     long long pc_wait = 0, pc_p1 = 0, pc_p2 = 0, pc_n = 0, pc_t0 = 0, pc_t1 = 0;
+    // projector epilogue (K8): the loop state is read once per thread, not per element
+    float pj_alpha = 0.f;
+    float *pj_x = nullptr, *pj_trace = nullptr;
+    int pj_n_cond = 0, pj_cond_mul = 1, pj_cond_row = -1;
+    if (p.proj_x) {
+      const LoopState *ls = p.ls;
+      const int step = ls->step;
+      pj_alpha = p.alpha_tab[step];
+      pj_x = ls->x;
+      float *trc = ls->trace;
+      pj_trace = trc ? trc + (size_t)(ls->n_steps - 1 - step) * ls->trace_stride : nullptr;
+      const unsigned fl = ls->flags;
+      pj_n_cond = ((fl & 1u) && !(fl & 4u)) ? ls->n_cond : 0;
+      const int per_batch = ls->cond_per_batch;
+      pj_cond_mul = per_batch ? ls->cond_B : 1;
+      pj_cond_row = per_batch ? ls->cond_row0 : -1;
+    }
     for (int tile = blockIdx.x + wg * gridDim.x; tile < total_tiles; tile += TC_EPI_WG * gridDim.x, it += TC_EPI_WG) {
       if (DAD_PROF_PTR(p)) pc_t0 = clock64();
       const int tm = tile / p.n_tiles_n, tn = tile - tm * p.n_tiles_n;
@@ -417,25 +434,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         if (valid && (!(DAD_DEBUG_BITS(p) & 4) || y[0] == 123.456f)) {
           if (p.proj_x) {
             // dynamics projector: y = x' + alpha (N x' + q), Diffuser-style inpainting, optional trace (policies.py:409-485,61-62)
-            const LoopState &ls = *p.ls;
-            const float alpha = p.alpha_tab[ls.step];
-            const int n_cond = ((ls.flags & 1u) && !(ls.flags & 4u)) ? ls.n_cond : 0;
+            // The chunk's x' values are fetched with 128-bit loads, inpainting is decided per (chunk, condition) from the
+            // column range [h_c T, h_c T + T) of the condition (no per-element division), results leave as 128-bit stores.
             const float *xr = p.proj_x + orow + c * CW;
-            float *o = ls.x + orow + c * CW;
-            float *tr = ls.trace ? ls.trace + (size_t)(ls.n_steps - 1 - ls.step) * ls.trace_stride + orow + c * CW : nullptr;
+            float *o = pj_x + orow + c * CW;
+            float *tr = pj_trace ? pj_trace + orow + c * CW : nullptr;
+            const bool full = nc + CW <= p.Cout;      // Cout = D is a multiple of 4 (the step kernels' float4 contract)
+            float xv[CW];
+            if (full) {
 #pragma unroll
-            for (int j = 0; j < CW; ++j) {
-              const int n = nc + j;
-              if (n < p.Cout) {
-                float v = xr[j] + alpha * y[j];
-                const int hh = n / p.T, tt = n - hh * p.T;
-                for (int cc = 0; cc < n_cond; ++cc)
-                  if (ls.cond_h[cc] == hh)
-                    v = p.cond_vals[((size_t)cc * (ls.cond_per_batch ? ls.cond_B : 1) +
-                                     (ls.cond_per_batch ? (ls.cond_row0 + b) : 0)) * p.T + tt];
-                o[j] = v;
-                if (tr) tr[j] = v;
+              for (int j = 0; j < CW; j += 4) {
+                const float4 x4 = __ldg(reinterpret_cast<const float4 *>(xr + j));
+                xv[j] = x4.x; xv[j + 1] = x4.y; xv[j + 2] = x4.z; xv[j + 3] = x4.w;
               }
+            } else {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) xv[j] = (nc + j < p.Cout) ? xr[j] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < CW; ++j) y[j] = fmaf(pj_alpha, y[j], xv[j]);
+            for (int cc = 0; cc < pj_n_cond; ++cc) {
+              const int base = nc - __ldg(&p.ls->cond_h[cc]) * p.T;      // column nc + j belongs to the condition iff 0 <= base + j < T
+              if (base + CW <= 0 || base >= p.T) continue;
+              const float *row = p.cond_vals + ((size_t)cc * pj_cond_mul + (pj_cond_row >= 0 ? pj_cond_row + b : 0)) * p.T;
+#pragma unroll
+              for (int j = 0; j < CW; ++j)
+                if ((unsigned)(base + j) < (unsigned)p.T) y[j] = row[base + j];
+            }
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < CW; j += 4) {
+                const float4 o4 = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+                *reinterpret_cast<float4 *>(o + j) = o4;
+                if (tr) *reinterpret_cast<float4 *>(tr + j) = o4;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < CW; ++j)
+                if (nc + j < p.Cout) {
+                  o[j] = y[j];
+                  if (tr) tr[j] = y[j];
+                }
             }
           } else if (p.out_f32) {
             float *o = reinterpret_cast<float *>(p.out) + orow + c * CW;

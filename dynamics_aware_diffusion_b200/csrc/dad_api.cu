@@ -109,9 +109,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 
 }  // namespace
 
-// Batch from which the dynamics projector runs on the tensor cores even though the fused SIMT kernel fits (D*D*4 B in
-// shared memory).  INT_MAX = never; set from the measured cross-over.
-constexpr int kProjTcMinBatch = INT_MAX;
+// Batch from which the dynamics projector runs on the tensor cores (pointwise kernel + bf16x3 tcgen05 GEMM, K8) even
+// though the fused SIMT kernel fits (D*D*4 B in shared memory, PointMaze D = 192).  Measured cross-over on a B200
+// (tools/projector_paths.py, isolated launches): B = 4096: 19.2 vs 17.9 us, 8192: 34.4 vs 20.0, 65536: 343 vs 108,
+// 262144: 2722 vs 387; below 4096 the single fused launch wins (9.6 vs 16.1 us at B = 512).
+constexpr int kProjTcMinBatch = 8192;
 
 struct dad_handle {
   dad_config cfg{};
@@ -148,7 +150,10 @@ struct dad_handle {
   // The fused SIMT projector (projector in shared memory) wins while the batch is small enough to be latency-bound; from
   // this batch on the tensor-core path (pointwise + bf16x3 GEMM) is used even when the fused kernel fits (measured
   // cross-over, tools/step_times.py).  force_proj_tc: measurement switch of dad_time_step_kernel (flag 0x200).
-  int proj_tc_min_batch = kProjTcMinBatch;
+  // dad_set_fp32_steps: reverse steps with index >= fp32_min_step take eps from this fp32 handle
+  dad_handle *companion = nullptr;
+  int fp32_min_step = INT_MAX;
+  int proj_tc_min_batch = tuning_env("DAD_PROJ_TC_MIN_B", kProjTcMinBatch);
   bool force_proj_tc = false;
   // conditions
   int n_cond = 0, cond_per_batch = 0, cond_B = 0;
@@ -1824,13 +1829,35 @@ int dad_sample(dad_handle *h, float *x, const float *noise_seq, uint64_t seed, u
       init_x_kernel<<<cdiv((size_t)Bc * D / 4, 256), 256, 0, st>>>(h->d_ls, h->d_cond, Bc, (int)D, h->cfg.transition_dim, draw ? 1 : 0);
       h->launches += 1;
     }
+    // leading steps routed through the fp32 companion (dad_set_fp32_steps): its U-Net reads x in place and leaves eps
+    // in OUR eps buffer, the rest of the step is ours.  Noise / trace slots and Philox slots are indexed by the step, so
+    // the split does not change the draws.
+    int done = 0;
+    if (h->companion && h->fp32_min_step < n_steps) {
+      const int lead = n_steps - std::max(h->fp32_min_step, 0);
+      for (; done < lead; ++done) {
+        const int i = n_steps - 1 - done;
+        const long long before = h->companion->launches;
+        if ((rc = dad_unet_forward(h->companion, ls.x, nullptr, i, h->d_eps, Bc, stream)))
+          DAD_FAIL(h, rc, "fp32 companion: %s", dad_last_error(h->companion));
+        ls.step = i;
+        if ((rc = set_loop_state(h, ls, st))) return rc;
+        h->counting = 0;
+        if ((rc = enqueue_step(h, h->d_eps, Bc, project, false, st))) return rc;
+        h->launches += h->counting + (h->companion->launches - before);
+      }
+      if (done == n_steps) continue;
+      ls.step = n_steps - done;       // every graph replay first decrements it
+      if ((rc = set_loop_state(h, ls, st))) return rc;
+    }
     // whole multiples of kStepsPerGraph through the multi-step graph, the remainder step by step
-    const int reps = std::min(n_steps, kStepsPerGraph);
+    const int left = n_steps - done;
+    const int reps = std::min(left, kStepsPerGraph);
     GraphEntry *ge = nullptr, *ge1 = nullptr;
     if ((rc = get_graph(h, Bc, project, reps, &ge))) return rc;
-    int done = 0;
+    const int done0 = done;
     for (; done + reps <= n_steps; done += reps) CK(h, cudaGraphLaunch(ge->exec, st));
-    h->launches += ge->kernels * (done / reps);
+    h->launches += ge->kernels * ((done - done0) / reps);
     if (done < n_steps) {
       if ((rc = get_graph(h, Bc, project, 1, &ge1))) return rc;
       for (; done < n_steps; ++done) { CK(h, cudaGraphLaunch(ge1->exec, st)); h->launches += ge1->kernels; }
@@ -2086,6 +2113,22 @@ int dad_sample_profile(dad_handle *h, float *x, uint64_t seed, uint64_t sample_o
   CK(h, cudaStreamSynchronize(st));
   for (int s = 0; s < n_steps; ++s) CK(h, cudaEventElapsedTime(&step_ms[s], ev[s], ev[s + 1]));
   for (auto &e : ev) cudaEventDestroy(e);
+  return DAD_OK;
+}
+
+int dad_set_fp32_steps(dad_handle *h, dad_handle *companion, int32_t min_step) {
+  if (!h) return DAD_ERR_INVALID;
+  if (!companion) { h->companion = nullptr; h->fp32_min_step = INT_MAX; return DAD_OK; }
+  if (companion == h || companion->bf16) DAD_FAIL(h, DAD_ERR_INVALID, "dad_set_fp32_steps: the companion must be another handle of fp32 precision");
+  if (!h->bf16) DAD_FAIL(h, DAD_ERR_INVALID, "dad_set_fp32_steps: this handle already computes in fp32");
+  const dad_config &a = h->cfg, &b = companion->cfg;
+  bool same = a.device == b.device && a.transition_dim == b.transition_dim && a.dim == b.dim && a.n_levels == b.n_levels &&
+              a.kernel_size == b.kernel_size && a.horizon == b.horizon && a.n_timesteps == b.n_timesteps;
+  for (int l = 0; same && l < a.n_levels; ++l) same = a.dim_mults[l] == b.dim_mults[l];
+  if (!same) DAD_FAIL(h, DAD_ERR_INVALID, "dad_set_fp32_steps: the companion was created for a different architecture / device");
+  if (min_step < 0) DAD_FAIL(h, DAD_ERR_INVALID, "dad_set_fp32_steps: min_step %d < 0", min_step);
+  h->companion = companion;
+  h->fp32_min_step = min_step;
   return DAD_OK;
 }
 

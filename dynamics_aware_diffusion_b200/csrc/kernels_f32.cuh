@@ -3,6 +3,7 @@
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
+#include "f32x2.cuh"
 
 namespace dad {
 
@@ -10,9 +11,14 @@ namespace dad {
 // Implicit-GEMM Conv1d / ConvTranspose1d-phase / 1x1 conv, fp32 in, fp32 accumulate.
 //   replaces nn.Conv1d / nn.ConvTranspose1d calls at temporal_unet.py:40,51,70,103,196
 //   weights: Wp[tap][c][n]  (n contiguous).
-// Tile 64 rows x 64 cols x 16 k, 256 threads, 4x4 outputs per thread.
+// Tile 128 rows x 64 cols x 16 k, 256 threads, 8x4 outputs per thread as 4 row pairs x 4 columns of packed fp32x2
+// accumulators (one FFMA2 = two IEEE fmas: the per-output accumulation order -- k ascending, one fma per k -- is the
+// same as a scalar loop's, so results do not depend on the tiling).  Shared-memory tiles are double-buffered and the
+// next tile's global loads are issued before the current tile is multiplied (one __syncthreads per k block).
+// This kernel is the 1e-5 parity mode AND the fp32 sibling that evaluates the ill-conditioned leading reverse step of
+// a bf16 model (dad_set_fp32_steps), i.e. one U-Net pass per plan sits in the timed region of the benchmark.
 // ------------------------------------------------------------------------------------------
-constexpr int F32_BM = 64, F32_BN = 64, F32_BK = 16;
+constexpr int F32_BM = 128, F32_BN = 64, F32_BK = 16;
 
 enum { EPI_BIAS = 0, EPI_PROJECT = 1 };
 
@@ -33,8 +39,8 @@ struct ConvF32Params {
 
 template <int EPI, bool VEC>
 __global__ void __launch_bounds__(256) conv_f32_kernel(const ConvF32Params p) {
-  __shared__ float As[F32_BK][F32_BM + 4];
-  __shared__ float Bs[F32_BK][F32_BN];
+  __shared__ __align__(16) float As[2][F32_BK][F32_BM + 4];
+  __shared__ __align__(16) float Bs[2][F32_BK][F32_BN];
   ptx::griddep_launch();
   ptx::griddep_wait();
   const ConvGeom &g = p.g;
@@ -43,10 +49,10 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const ConvF32Params p) {
   const int M = p.B * g.L_out;
   const int m0 = blockIdx.x * F32_BM, n0 = blockIdx.y * F32_BN;
   const int tid = threadIdx.x;
-  const int ty = tid >> 4, tx = tid & 15;
+  const int ty = tid >> 4, tx = tid & 15;        // rows ty*8 .. +7, columns tx*4 .. +3
 
-  // A loader: one row, 4 consecutive k per thread.
-  const int a_row = tid >> 2, a_k = (tid & 3) * 4;
+  // A loader: one row, two groups of 4 consecutive k per thread.
+  const int a_row = tid >> 1, a_k = (tid & 1) * 8;
   const int am = m0 + a_row;
   const bool a_ok = am < M;
   const int ab = a_ok ? am / g.L_out : 0;
@@ -54,17 +60,20 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const ConvF32Params p) {
   // B loader: one k, 4 consecutive n per thread.
   const int b_k = tid >> 4, b_n = (tid & 15) * 4;
 
-  float acc[4][4];
+  f32x2 acc[4][4];                                 // [row pair][column]: rows (ty*8 + 2i, ty*8 + 2i + 1)
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = pk2(0.f, 0.f);
 
-  for (int k0 = 0; k0 < K; k0 += F32_BK) {
-    // ---- A tile
-    float av[4] = {0.f, 0.f, 0.f, 0.f};
-    if (a_ok) {
-      const int kk = k0 + a_k;
+  float av[8], bv[4];
+  auto load_tile = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float *a4 = av + 4 * q;
+      a4[0] = a4[1] = a4[2] = a4[3] = 0.f;
+      if (!a_ok) continue;
+      const int kk = k0 + a_k + 4 * q;
       if (VEC) {
         if (kk < K) {
           const int tap = kk / Cin, c = kk - tap * Cin;
@@ -73,7 +82,7 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const ConvF32Params p) {
             const float *src = (c < g.C1) ? p.in1 + ((size_t)(ab * g.L_in + li) * g.C1 + c)
                                           : p.in2 + ((size_t)(ab * g.L_in + li) * g.C2 + (c - g.C1));
             const float4 v = *reinterpret_cast<const float4 *>(src);
-            av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
+            a4[0] = v.x; a4[1] = v.y; a4[2] = v.z; a4[3] = v.w;
           }
         }
       } else {
@@ -84,42 +93,55 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const ConvF32Params p) {
             const int tap = kj / Cin, c = kj - tap * Cin;
             const int li = alo * g.in_stride + g.tap_off[tap];
             if (li >= 0 && li < g.L_in)
-              av[j] = (c < g.C1) ? p.in1[(size_t)(ab * g.L_in + li) * g.C1 + c]
+              a4[j] = (c < g.C1) ? p.in1[(size_t)(ab * g.L_in + li) * g.C1 + c]
                                  : p.in2[(size_t)(ab * g.L_in + li) * g.C2 + (c - g.C1)];
           }
         }
       }
     }
-    // ---- B tile
-    float bv[4] = {0.f, 0.f, 0.f, 0.f};
-    {
-      const int kk = k0 + b_k, n = n0 + b_n;
-      if (kk < K) {
-        const float *src = p.w + (size_t)kk * g.Cout + n;
-        if (VEC && n + 3 < g.Cout) {
-          const float4 v = *reinterpret_cast<const float4 *>(src);
-          bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
-        } else {
+    bv[0] = bv[1] = bv[2] = bv[3] = 0.f;
+    const int kk = k0 + b_k, n = n0 + b_n;
+    if (kk < K) {
+      const float *src = p.w + (size_t)kk * g.Cout + n;
+      if (VEC && n + 3 < g.Cout) {
+        const float4 v = *reinterpret_cast<const float4 *>(src);
+        bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+      } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (n + j < g.Cout) bv[j] = src[j];
-        }
+        for (int j = 0; j < 4; ++j)
+          if (n + j < g.Cout) bv[j] = src[j];
       }
     }
-    __syncthreads();
+  };
+  auto store_tile = [&](int buf) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) As[a_k + j][a_row] = av[j];
-    *reinterpret_cast<float4 *>(&Bs[b_k][b_n]) = make_float4(bv[0], bv[1], bv[2], bv[3]);
-    __syncthreads();
+    for (int j = 0; j < 8; ++j) As[buf][a_k + j][a_row] = av[j];
+    *reinterpret_cast<float4 *>(&Bs[buf][b_k][b_n]) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+  };
+
+  load_tile(0);
+  store_tile(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += F32_BK) {
+    const bool more = k0 + F32_BK < K;
+    if (more) load_tile(k0 + F32_BK);              // global loads in flight while this tile is multiplied
 #pragma unroll
     for (int k = 0; k < F32_BK; ++k) {
-      const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
-      const float ar[4] = {a.x, a.y, a.z, a.w}, br[4] = {b.x, b.y, b.z, b.w};
+      const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4 *>(&As[buf][k][ty * 8 + 4]);
+      const float4 b = *reinterpret_cast<const float4 *>(&Bs[buf][k][tx * 4]);
+      const f32x2 ar[4] = {pk2(a0.x, a0.y), pk2(a0.z, a0.w), pk2(a1.x, a1.y), pk2(a1.z, a1.w)};
+      const f32x2 br[4] = {pk2(b.x, b.x), pk2(b.y, b.y), pk2(b.z, b.z), pk2(b.w, b.w)};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = ffma2(ar[i], br[j], acc[i][j]);
+    }
+    if (more) {
+      store_tile(buf ^ 1);                         // the other buffer: its readers finished before the last barrier
+      __syncthreads();
+      buf ^= 1;
     }
   }
 
@@ -133,8 +155,8 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const ConvF32Params p) {
     n_cond = ((ls.flags & 1u) && !(ls.flags & 4u)) ? ls.n_cond : 0;  // project -> inpaint order
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ty * 8 + i;
     if (m >= M) continue;
     const int b = m / g.L_out, lo = m - b * g.L_out;
     const size_t orow = ((size_t)b * (g.L_out * g.out_mul) + lo * g.out_mul + g.out_phase) * g.Cout;
@@ -142,7 +164,9 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const ConvF32Params p) {
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
       if (n >= g.Cout) continue;
-      float v = acc[i][j] + p.bias[n];
+      float r0, r1;
+      upk2(acc[i >> 1][j], r0, r1);
+      float v = ((i & 1) ? r1 : r0) + p.bias[n];
       if (EPI == EPI_BIAS) {
         if (p.residual) v += p.residual[orow + n];
       } else {

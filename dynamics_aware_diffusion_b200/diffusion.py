@@ -88,13 +88,13 @@ class GaussianDiffusion(nn.Module):
         self.loss_type = loss_type
         # the stand-alone model(x, t) call shares the engine (and its time tables) with the sampling loop
         model._n_timesteps = int(betas.shape[0])
-        # bf16 models: evaluate the ILL-CONDITIONED leading reverse steps with the fp32 kernels.  With the cosine schedule
+        # bf16 models evaluate the ILL-CONDITIONED leading reverse steps with the fp32 kernels.  With the cosine schedule
         # beta_{S-1} is clipped to 0.9999 (diffusion.py:41), so the first reverse step has d(mean)/d(eps) = 99.98 and any
         # bf16 evaluation of eps (ours 8e-3 relative, stock autocast 1.1e-2) shows up as 1.3-2e-2 on x at that one step;
-        # every other step amplifies eps errors by < 1.5.  True keeps every step within the 1e-2 bf16 tolerance at the
-        # price of ONE fp32 U-Net pass per sampling loop (fp32 SIMT kernels: ~40 bf16 steps' worth at B=4096); the
-        # default, False, runs every step on the tensor cores.
-        self.fp32_ill_conditioned_steps = False
+        # every other step amplifies eps errors by < 1.5.  True (the default) keeps EVERY step within BASELINE.json's 1e-2
+        # bf16 tolerance at the price of ONE fp32 U-Net pass per sampling loop (inside dad_sample, see
+        # dad_set_fp32_steps); False runs every step on the tensor cores.  A no-op for the linear schedule.
+        self.fp32_ill_conditioned_steps = True
         self._ill_cache = None
 
     # ---- native plumbing ------------------------------------------------------------------------
@@ -117,21 +117,41 @@ class GaussianDiffusion(nn.Module):
             eng.set_schedule(self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod,
                              self.posterior_mean_coef1, self.posterior_mean_coef2, self.posterior_log_variance_clipped)
             ent["schedule_owner"] = tag
+        if eng.precision == "bf16":
+            # the fp32 sibling for the ill-conditioned steps (dad_set_fp32_steps): same weights, same schedule
+            first = self.ill_conditioned_min_step() if self.fp32_ill_conditioned_steps else int(self.betas.shape[0])
+            if first < int(self.betas.shape[0]):
+                eng32 = self.engine(horizon, device, precision="fp32")
+                if eng._companion is None or eng._companion[0] is not eng32 or eng._companion[1] != first:
+                    eng.set_fp32_steps(eng32, first)
+            elif eng._companion is not None:
+                eng.set_fp32_steps(None)
         return eng
 
-    def ill_conditioned_prefix(self, n_steps=None) -> int:
-        """How many LEADING reverse steps (i = S-1, S-2, ...) amplify an eps error by more than 10x:
-        d(mean)/d(eps) = posterior_mean_coef1[i] * sqrt_recipm1_alphas_cumprod[i].  1 for the cosine schedule, 0 for the
-        linear one."""
-        S = int(n_steps or self.n_timesteps)
-        tag = (self._schedule_version(), S)
+    def eps_engine(self, eng, step):
+        """The engine that evaluates the U-Net for reverse step `step` on the per-step entry points (p_sample,
+        p_sample_with_guidance, host loops): the fp32 sibling for an ill-conditioned step of a bf16 model, else `eng`."""
+        comp = eng._companion
+        return comp[0] if (comp is not None and int(step) >= comp[1]) else eng
+
+    def ill_conditioned_min_step(self) -> int:
+        """First index of the TRAILING run of step indices that amplify an eps error by more than 10x:
+        d(mean)/d(eps) = posterior_mean_coef1[i] * sqrt_recipm1_alphas_cumprod[i].  len - 1 for the cosine schedule,
+        len (none) for the linear one."""
+        tag = self._schedule_version()
         if self._ill_cache is None or self._ill_cache[0] != tag:
-            amp = (self.posterior_mean_coef1 * self.sqrt_recipm1_alphas_cumprod).detach().cpu()[:S]
-            k = 0
-            while k < S and float(amp[S - 1 - k]) > 10.0:
-                k += 1
-            self._ill_cache = (tag, k)
+            amp = (self.posterior_mean_coef1 * self.sqrt_recipm1_alphas_cumprod).detach().cpu()
+            i = int(amp.shape[0])
+            while i > 0 and float(amp[i - 1]) > 10.0:
+                i -= 1
+            self._ill_cache = (tag, i)
         return self._ill_cache[1]
+
+    def ill_conditioned_prefix(self, n_steps=None) -> int:
+        """How many LEADING reverse steps of a loop of `n_steps` steps (i = n_steps-1, n_steps-2, ...) are ill-conditioned
+        (see ill_conditioned_min_step): 1 for the full cosine schedule, 0 for the linear one or a shortened loop."""
+        S = int(n_steps or self.n_timesteps)
+        return max(0, S - self.ill_conditioned_min_step())
 
     def _check_steps(self):
         if self.n_timesteps > self.betas.shape[0]:
@@ -156,7 +176,16 @@ class GaussianDiffusion(nn.Module):
 
     def p_mean_variance(self, x, t) -> Tuple[torch.Tensor, torch.Tensor]:
         """(model_mean, posterior_log_variance (B,1,1)) as diffusion.py:182-203; the model call is native."""
-        out = self.model(x, t)
+        out = None
+        if x.is_cuda and self.model.precision != "fp32" and self.fp32_ill_conditioned_steps and \
+                self.ill_conditioned_min_step() < int(self.betas.shape[0]):
+            # a whole batch at an ill-conditioned step of a bf16 model: eps from the fp32 sibling, as in the loops
+            lo, hi = (int(v) for v in torch.aminmax(t.reshape(-1)))
+            eng = self.engine(x.shape[1], x.device)
+            if lo == hi and self.eps_engine(eng, lo) is not eng:
+                out = self.eps_engine(eng, lo).unet_forward(x.contiguous().float(), step=lo)
+        if out is None:
+            out = self.model(x, t)
         x_recon = self.predict_start_from_noise(x, t, out) if self.predict_epsilon else out
         if self.clip_denoised:
             x_recon = torch.clamp(x_recon, -1.0, 1.0)
@@ -169,7 +198,7 @@ class GaussianDiffusion(nn.Module):
         step = uniform_timestep(t)
         eng = self.engine(x.shape[1], x.device)
         xc = x.contiguous().float()
-        eps = eng.unet_forward(xc, step=step)
+        eps = self.eps_engine(eng, step).unet_forward(xc, step=step)
         noise = torch.randn_like(x)
         out = xc.clone()
         return eng.step(out, eps, step, noise=noise.contiguous())
@@ -214,23 +243,9 @@ def _run_loop(diffusion, x, noise, rng, seed, flags, return_trace=False, sample_
     trace = torch.empty((S,) + tuple(x.shape), device=x.device) if return_trace else None
     torch.cuda.nvtx.range_push("sample_loop B=%d S=%d" % (x.shape[0], S))
     try:
-        lead = 0
-        if diffusion.fp32_ill_conditioned_steps and eng.precision == "bf16":
-            # leading ill-conditioned steps: eps from the fp32 kernels, the rest of the step (and of the loop) unchanged.
-            # Philox slots and noise / trace slots are indexed by the step, so the split does not change the draws.
-            lead = diffusion.ill_conditioned_prefix(S)
-            if lead:
-                eng32 = diffusion.engine(x.shape[1], x.device, precision="fp32")
-                for k in range(lead):
-                    i = S - 1 - k
-                    eps = eng32.unet_forward(x, step=i)
-                    eng.step(x, eps, i, noise=None if noise is None else noise[k], flags=flags, seed=seed,
-                             sample_offset=sample_offset)
-                    if trace is not None:
-                        trace[k].copy_(x)
-        if S - lead > 0:
-            eng.sample(x, S - lead, noise_seq=None if noise is None else noise[lead:], flags=flags, seed=seed,
-                       sample_offset=sample_offset, trace=None if trace is None else trace[lead:])
+        # the ill-conditioned leading steps of a bf16 model go through the fp32 sibling INSIDE dad_sample
+        # (dad_set_fp32_steps, attached by engine())
+        eng.sample(x, S, noise_seq=noise, flags=flags, seed=seed, sample_offset=sample_offset, trace=trace)
     finally:
         torch.cuda.nvtx.range_pop()
     return (x, trace) if return_trace else x

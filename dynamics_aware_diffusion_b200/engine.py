@@ -54,6 +54,7 @@ class Engine:
         self._keep = []          # tensors whose device memory the handle may still read asynchronously
         self.has_projector = False
         self.projector_tag = None        # who pushed the projector that is loaded now (DynamicsAwarePolicy._push_projector)
+        self._companion = None           # (fp32 Engine, min_step) attached with set_fp32_steps
 
     def close(self):
         if getattr(self, "handle", None) and self.handle.value:
@@ -275,6 +276,16 @@ class Engine:
 
     def launch_count(self):
         return int(self.lib.dad_launch_count(self.handle))
+
+    def set_fp32_steps(self, companion, min_step=0):
+        """Reverse steps with index >= min_step take eps from `companion` (an fp32 Engine of the same architecture and
+        weights) inside sample() / sample_host(); None detaches.  This engine keeps the companion alive."""
+        if companion is None:
+            self._ck(self.lib.dad_set_fp32_steps(self.handle, None, 0))
+            self._companion = None
+            return
+        self._ck(self.lib.dad_set_fp32_steps(self.handle, companion.handle, int(min_step)))
+        self._companion = (companion, int(min_step))
 
     def set_latency_batch(self, max_b):
         """Batches <= max_b run the latency kernels (get_action's single plan); 0 = throughput kernels only."""

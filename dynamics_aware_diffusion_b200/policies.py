@@ -82,7 +82,7 @@ class GuidedPolicy(nn.Module):
         step = uniform_timestep(t)
         eng = self._engine(x.device)
         xc = x.contiguous().float()
-        eps = eng.unet_forward(xc, step=step)
+        eps = self.diffusion.eps_engine(eng, step).unet_forward(xc, step=step)
         grad = self._guidance_grad(xc, t)
         noise = torch.randn_like(xc)
         flags = 0
@@ -108,10 +108,6 @@ class GuidedPolicy(nn.Module):
             flags |= N.FLAG_CONDITIONS
         guided = self.guide_fn is not None and self.guide_weight > 0
         if not guided:
-            if conditions and self.diffusion.fp32_ill_conditioned_steps:
-                # x_S is inpainted before the first model call (policies.py:137-138); dad_sample does it in-kernel, the
-                # fp32 pre-steps need it done here
-                x = self.apply_conditions(x, {h: torch.as_tensor(v, device=device) for h, v in conditions.items()})
             return _run_loop(self.diffusion, x, noise, rng, seed, flags, return_trace, sample_offset)
         # guided: autograd supplies the gradient each step, the rest stays native
         S = self.diffusion.n_timesteps
@@ -130,7 +126,7 @@ class GuidedPolicy(nn.Module):
         trace = []
         for k, i in enumerate(reversed(range(S))):
             t = torch.full((batch_size,), i, device=device, dtype=torch.long)
-            eps = eng.unet_forward(x, step=i)
+            eps = self.diffusion.eps_engine(eng, i).unet_forward(x, step=i)
             grad = self._guidance_grad(x, t)
             if noise is not None:
                 z = noise[k].to(device, torch.float32).contiguous()
@@ -200,7 +196,6 @@ class GuidedPolicy(nn.Module):
             ent["epoch"] = eng.graph_epoch()
             self._guided_graphs = {key: ent}       # one captured step alive at a time
         ent["x"].copy_(x_init)
-        ent["t"].fill_(S)
         trace = torch.empty((S,) + tuple(x_init.shape), device=device) if return_trace else None
         if mode == "seq":
             zseq = noise.to(device, torch.float32).contiguous()
@@ -208,11 +203,34 @@ class GuidedPolicy(nn.Module):
                 raise ValueError("noise must be (n_timesteps, B, H, T)")
         else:
             zseq = ent["z"]
-        eng.loop_begin(ent["x"], S, noise=zseq, noise_single=(mode == "torch"), grad=ent["grad"],
-                       guide_w=float(self.guide_weight), flags=flags, seed=seed, sample_offset=sample_offset, trace=trace)
-        for _ in range(S):
-            ent["graph"].replay()
-        eng.loop_replayed(S)
+        # ill-conditioned leading steps of a bf16 model (GaussianDiffusion.fp32_ill_conditioned_steps): per-step host
+        # path with eps from the fp32 sibling; the captured step replays the rest.  Slots are indexed by the step, so
+        # the remaining S - lead steps see noise[lead:], trace[lead:] and the same Philox draws.
+        lead = 0
+        while lead < S and self.diffusion.eps_engine(eng, S - 1 - lead) is not eng:
+            i = S - 1 - lead
+            ent["t"].fill_(i)
+            eps = self.diffusion.eps_engine(eng, i).unet_forward(ent["x"], step=i)
+            if mode == "seq":
+                z = zseq[lead]
+            elif mode == "torch":
+                z = ent["z"].normal_()
+            else:
+                z = None
+            eng.step(ent["x"], eps, i, noise=z, grad=self._guidance_grad(ent["x"], ent["t"]),
+                     guide_w=float(self.guide_weight), flags=flags, seed=seed, sample_offset=sample_offset)
+            if trace is not None:
+                trace[lead].copy_(ent["x"])
+            lead += 1
+        rest = S - lead
+        if rest > 0:
+            ent["t"].fill_(rest)
+            eng.loop_begin(ent["x"], rest, noise=zseq if mode != "seq" else zseq[lead:], noise_single=(mode == "torch"),
+                           grad=ent["grad"], guide_w=float(self.guide_weight), flags=flags, seed=seed,
+                           sample_offset=sample_offset, trace=None if trace is None else trace[lead:])
+            for _ in range(rest):
+                ent["graph"].replay()
+            eng.loop_replayed(rest)
         out = ent["x"].clone()
         return (out, trace) if return_trace else out
 

@@ -171,6 +171,15 @@ int64_t dad_launch_count(const dad_handle *h);
  * latency kernels; the default is 24, about where the throughput kernels take over on a B200 (or the
  * DAD_SMALL_MAX_B environment variable).  bf16 mode only. */
 int dad_set_latency_batch(dad_handle *h, int32_t max_b);
+/* Mixed precision across the reverse process.  A bf16 handle evaluates the U-Net of the reverse steps with index >=
+ * `min_step` through `companion`, an fp32-precision handle of the same architecture with the same weights loaded (the
+ * rest of those steps -- posterior mean, noise, projector, inpainting -- stays in `h`).  With the cosine schedule
+ * beta_{S-1} is clipped to 0.9999 (diffusion.py:41): the first reverse step has d(mean)/d(eps) = 99.98, so ANY bf16
+ * evaluation of eps (this library 8e-3 relative, stock torch.autocast 1.1e-2) shows up as 1.3-2e-2 on x at that one
+ * step; every other step amplifies eps errors by < 1.5.  min_step = S-1 keeps every step within BASELINE.json's 1e-2
+ * at the price of one fp32 pass per plan.  Applies to dad_sample / dad_sample_host; the per-step entry points take
+ * whatever eps the caller computed.  companion = NULL detaches.  The caller keeps `companion` alive while attached. */
+int dad_set_fp32_steps(dad_handle *h, dad_handle *companion, int32_t min_step);
 /* How the stride-1 convolutions of the U-Net (temporal_unet.py:106-122, 214-237) are grouped into launches, bf16
  * mode: 3 (default) = one persistent conv_chain launch per run of ResidualTemporalBlocks of one level (their convs
  * synchronise through per-sample-tile counters instead of kernel boundaries), 2 = one launch per block, 1 = one

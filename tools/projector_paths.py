@@ -12,6 +12,7 @@ H, T = 32, 6
 Bmax = 262144
 net = TemporalUnet(T, dim=64, dim_mults=(1,), precision="bf16", max_batch=Bmax)
 dif = GaussianDiffusion(net, horizon=H, observation_dim=4, action_dim=2, n_timesteps=100).to(dev)
+dif.fp32_ill_conditioned_steps = False      # only the step kernels run here
 pol, eng, flags, _, _ = bench.attach_policy(dif, dict(bench.WORKLOADS["pointmaze"], S=100), dev, Bmax)
 for B in [int(a) for a in sys.argv[1:]] or [512, 1024, 2048, 4096, 8192, 16384, 65536, 262144]:
     row = []
