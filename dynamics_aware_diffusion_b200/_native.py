@@ -21,7 +21,7 @@ EXPORTS = (
     "dad_loop_begin", "dad_loop_unet", "dad_loop_step", "dad_graph_epoch", "dad_loop_replayed",
     "dad_build_projection_matrix", "dad_fit_linear_dynamics", "dad_dynamics_residual",
     "dad_sample_profile", "dad_layer_count", "dad_layer_info", "dad_time_layer", "dad_time_step_kernel",
-    "dad_set_fusion", "dad_unit_count", "dad_unit_info", "dad_time_unit", "dad_debug_counters", "dad_set_fp32_steps",
+    "dad_set_fusion", "dad_unit_count", "dad_unit_info", "dad_time_unit", "dad_debug_counters", "dad_set_fp32_steps", "dad_set_fp32_math",
 )
 
 
@@ -97,6 +97,7 @@ def lib():
     L.dad_launch_count.restype = ctypes.c_int64
     L.dad_set_latency_batch.argtypes = [vp, ctypes.c_int32]
     L.dad_set_fp32_steps.argtypes = [vp, vp, ctypes.c_int32]
+    L.dad_set_fp32_math.argtypes = [vp, ctypes.c_int32]
     L.dad_loop_begin.argtypes = [vp, vp, vp, ctypes.c_int32, vp, ctypes.c_float, ctypes.c_uint64, ctypes.c_uint64,
                                  ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32, vp, vp]
     L.dad_loop_unet.argtypes = [vp, ctypes.c_int32, vp]

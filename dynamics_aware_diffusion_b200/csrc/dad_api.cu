@@ -150,6 +150,7 @@ struct dad_handle {
   // The fused SIMT projector (projector in shared memory) wins while the batch is small enough to be latency-bound; from
   // this batch on the tensor-core path (pointwise + bf16x3 GEMM) is used even when the fused kernel fits (measured
   // cross-over, tools/step_times.py).  force_proj_tc: measurement switch of dad_time_step_kernel (flag 0x200).
+  int f32_math = 0;                  // dad_set_fp32_math: 0 IEEE fp32 SIMT, 1 TF32 tensor cores, 2 3xTF32
   // dad_set_fp32_steps: reverse steps with index >= fp32_min_step take eps from this fp32 handle
   dad_handle *companion = nullptr;
   int fp32_min_step = INT_MAX;
@@ -1058,7 +1059,11 @@ int enqueue_f32(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
   p.B = B;
   const bool vec = (op.g.C1 % 4 == 0) && (op.g.C2 % 4 == 0) && (op.g.Cout % 4 == 0);
   dim3 grid(cdiv((long long)B * op.g.L_out, F32_BM), cdiv(op.g.Cout, F32_BN));
-  if (vec) launch_k(conv_f32_kernel<EPI_BIAS, true>, grid, dim3(256), 0, st, 1, p);
+  // dad_set_fp32_math: the tensor-core variants take the layers whose channel counts they are written for
+  const bool tf = h->f32_math != 0 && vec && (op.g.Cout % 8 == 0);
+  if (tf && h->f32_math == 2) launch_k(conv_tf32_kernel<true>, grid, dim3(256), 0, st, 1, p);
+  else if (tf) launch_k(conv_tf32_kernel<false>, grid, dim3(256), 0, st, 1, p);
+  else if (vec) launch_k(conv_f32_kernel<EPI_BIAS, true>, grid, dim3(256), 0, st, 1, p);
   else launch_k(conv_f32_kernel<EPI_BIAS, false>, grid, dim3(256), 0, st, 1, p);
   h->counting += 1;
   if (gn) {
@@ -2129,6 +2134,13 @@ int dad_set_fp32_steps(dad_handle *h, dad_handle *companion, int32_t min_step) {
   if (min_step < 0) DAD_FAIL(h, DAD_ERR_INVALID, "dad_set_fp32_steps: min_step %d < 0", min_step);
   h->companion = companion;
   h->fp32_min_step = min_step;
+  return DAD_OK;
+}
+
+int dad_set_fp32_math(dad_handle *h, int32_t mode) {
+  if (!h || mode < 0 || mode > 2) return DAD_ERR_INVALID;
+  if (h->bf16) DAD_FAIL(h, DAD_ERR_INVALID, "dad_set_fp32_math applies to fp32-precision handles");
+  h->f32_math = mode;
   return DAD_OK;
 }
 

@@ -185,6 +185,184 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const ConvF32Params p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// The same implicit GEMM on the legacy tensor path: mma.sync.m16n8k8 TF32 operands, fp32 accumulate, fp32 activations
+// in and out.  Used by the fp32 SIBLING of a bf16 model for the ill-conditioned leading reverse step
+// (dad_set_fp32_steps + dad_set_fp32_math): that step needs eps several times more accurate than bf16 delivers, not
+// IEEE fp32, and the SIMT kernel above makes it cost ~5 % of a 500-step plan.
+//   X3 = false: operands rounded to TF32 with round-to-nearest when they enter shared memory (10-bit mantissa vs
+//               bf16's 7, and activations stay fp32 between layers);
+//   X3 = true : 3xTF32 error compensation (a_lo b_hi + a_hi b_lo + a_hi b_hi): fp32-level accuracy at 3 MMAs per step.
+// Tile 128 x 64 x 16, 8 warps as 4 (M) x 2 (N), each 32 x 32 = 2 x 4 MMA tiles.  Shared-memory strides 136 / 72 floats
+// make every fragment load bank-conflict-free.  Layers with channel counts that are not multiples of 4 / 8 (the first
+// conv, the head) stay on the SIMT kernel.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cvt_tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32_1688(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <bool X3>
+__global__ void __launch_bounds__(256) conv_tf32_kernel(const ConvF32Params p) {
+  constexpr int SA = F32_BM + 8, SB = F32_BN + 8;
+  __shared__ __align__(16) float As[2][F32_BK][SA];
+  __shared__ __align__(16) float Bs[2][F32_BK][SB];
+  ptx::griddep_launch();
+  ptx::griddep_wait();
+  const ConvGeom &g = p.g;
+  const int Cin = g.C1 + g.C2;
+  const int K = g.taps * Cin;
+  const int M = p.B * g.L_out;
+  const int m0 = blockIdx.x * F32_BM, n0 = blockIdx.y * F32_BN;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+  const int gid = lane >> 2, tig = lane & 3;
+
+  const int a_row = tid >> 1, a_k = (tid & 1) * 8;
+  const int am = m0 + a_row;
+  const bool a_ok = am < M;
+  const int ab = a_ok ? am / g.L_out : 0;
+  const int alo = a_ok ? am - ab * g.L_out : 0;
+  const int b_k = tid >> 4, b_n = (tid & 15) * 4;
+
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+
+  float av[8], bv[4];
+  auto load_tile = [&](int k0) {       // channel counts are multiples of 4 here (the host routes the others to the SIMT kernel)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float *a4 = av + 4 * q;
+      a4[0] = a4[1] = a4[2] = a4[3] = 0.f;
+      const int kk = k0 + a_k + 4 * q;
+      if (a_ok && kk < K) {
+        const int tap = kk / Cin, c = kk - tap * Cin;
+        const int li = alo * g.in_stride + g.tap_off[tap];
+        if (li >= 0 && li < g.L_in) {
+          const float *src = (c < g.C1) ? p.in1 + ((size_t)(ab * g.L_in + li) * g.C1 + c)
+                                        : p.in2 + ((size_t)(ab * g.L_in + li) * g.C2 + (c - g.C1));
+          const float4 v = *reinterpret_cast<const float4 *>(src);
+          a4[0] = v.x; a4[1] = v.y; a4[2] = v.z; a4[3] = v.w;
+        }
+      }
+    }
+    bv[0] = bv[1] = bv[2] = bv[3] = 0.f;
+    const int kk = k0 + b_k, n = n0 + b_n;
+    if (kk < K && n + 3 < g.Cout) {
+      const float4 v = *reinterpret_cast<const float4 *>(p.w + (size_t)kk * g.Cout + n);
+      bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+    }
+  };
+  auto rnd = [](float x) -> float { return X3 ? x : __uint_as_float(cvt_tf32_rn(x)); };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) As[buf][a_k + j][a_row] = rnd(av[j]);
+    *reinterpret_cast<float4 *>(&Bs[buf][b_k][b_n]) = make_float4(rnd(bv[0]), rnd(bv[1]), rnd(bv[2]), rnd(bv[3]));
+  };
+
+  load_tile(0);
+  store_tile(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += F32_BK) {
+    const bool more = k0 + F32_BK < K;
+    if (more) load_tile(k0 + F32_BK);
+#pragma unroll
+    for (int kk = 0; kk < F32_BK; kk += 8) {
+      float af[2][4], bf[4][2];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int r = wm + mi * 16 + gid;
+        af[mi][0] = As[buf][kk + tig][r];
+        af[mi][1] = As[buf][kk + tig][r + 8];
+        af[mi][2] = As[buf][kk + tig + 4][r];
+        af[mi][3] = As[buf][kk + tig + 4][r + 8];
+      }
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int c = wn + ni * 8 + gid;
+        bf[ni][0] = Bs[buf][kk + tig][c];
+        bf[ni][1] = Bs[buf][kk + tig + 4][c];
+      }
+      if constexpr (X3) {
+        uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            ah[mi][e] = cvt_tf32_rn(af[mi][e]);
+            al[mi][e] = cvt_tf32_rn(af[mi][e] - __uint_as_float(ah[mi][e]));
+          }
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            bh[ni][e] = cvt_tf32_rn(bf[ni][e]);
+            bl[ni][e] = cvt_tf32_rn(bf[ni][e] - __uint_as_float(bh[ni][e]));
+          }
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) {
+            mma_tf32_1688(acc[mi][ni], al[mi], bh[ni][0], bh[ni][1]);      // small terms first
+            mma_tf32_1688(acc[mi][ni], ah[mi], bl[ni][0], bl[ni][1]);
+            mma_tf32_1688(acc[mi][ni], ah[mi], bh[ni][0], bh[ni][1]);
+          }
+      } else {
+        uint32_t au[2][4];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) au[mi][e] = __float_as_uint(af[mi][e]);
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni)
+            mma_tf32_1688(acc[mi][ni], au[mi], __float_as_uint(bf[ni][0]), __float_as_uint(bf[ni][1]));
+      }
+    }
+    if (more) {
+      store_tile(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+  // ---- epilogue: bias (+ residual); c0/c1 = (row gid, cols 2 tig, 2 tig + 1), c2/c3 = row gid + 8
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int m = m0 + wm + mi * 16 + gid + hh * 8;
+      if (m >= M) continue;
+      const int b = m / g.L_out, lo = m - b * g.L_out;
+      const size_t orow = ((size_t)b * (g.L_out * g.out_mul) + lo * g.out_mul + g.out_phase) * g.Cout;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int n = n0 + wn + ni * 8 + 2 * tig;
+        if (n + 1 >= g.Cout + 1) continue;               // Cout is even here
+        float2 v = make_float2(acc[mi][ni][2 * hh] + p.bias[n], acc[mi][ni][2 * hh + 1] + p.bias[n + 1]);
+        if (p.residual) {
+          const float2 r = *reinterpret_cast<const float2 *>(p.residual + orow + n);
+          v.x += r.x;
+          v.y += r.y;
+        }
+        *reinterpret_cast<float2 *>(p.out + orow + n) = v;
+      }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // GroupNorm(8) + Mish (+ time bias | + residual), fp32.  One block per (sample, group).
 //   temporal_unet.py:71-72 (GN, Mish), :117 (time add), :122 (residual add)
 // ------------------------------------------------------------------------------------------

@@ -55,6 +55,7 @@ class Engine:
         self.has_projector = False
         self.projector_tag = None        # who pushed the projector that is loaded now (DynamicsAwarePolicy._push_projector)
         self._companion = None           # (fp32 Engine, min_step) attached with set_fp32_steps
+        self.fp32_math = "fp32"
 
     def close(self):
         if getattr(self, "handle", None) and self.handle.value:
@@ -286,6 +287,14 @@ class Engine:
             return
         self._ck(self.lib.dad_set_fp32_steps(self.handle, companion.handle, int(min_step)))
         self._companion = (companion, int(min_step))
+
+    FP32_MATH = {"fp32": 0, "tf32": 1, "tf32x3": 2}
+
+    def set_fp32_math(self, mode):
+        """fp32-precision engines: 'fp32' IEEE SIMT (default, the 1e-5 parity mode), 'tf32' TF32 operands on the tensor
+        cores (fp32 accumulate, fp32 activations), 'tf32x3' 3xTF32 error compensation."""
+        self._ck(self.lib.dad_set_fp32_math(self.handle, self.FP32_MATH[mode]))
+        self.fp32_math = mode
 
     def set_latency_batch(self, max_b):
         """Batches <= max_b run the latency kernels (get_action's single plan); 0 = throughput kernels only."""

@@ -180,6 +180,11 @@ int dad_set_latency_batch(dad_handle *h, int32_t max_b);
  * at the price of one fp32 pass per plan.  Applies to dad_sample / dad_sample_host; the per-step entry points take
  * whatever eps the caller computed.  companion = NULL detaches.  The caller keeps `companion` alive while attached. */
 int dad_set_fp32_steps(dad_handle *h, dad_handle *companion, int32_t min_step);
+/* Arithmetic of an fp32-precision handle's convolutions: 0 (default) IEEE fp32 on the SIMT pipes -- the 1e-5 parity mode;
+ * 1 TF32 operands (round-to-nearest) on the tensor cores with fp32 accumulation and fp32 activations; 2 3xTF32 error
+ * compensation (fp32-level accuracy).  1 is what a bf16 model's fp32 companion needs for the ill-conditioned step
+ * (eps several times more accurate than bf16) at a fraction of the SIMT cost. */
+int dad_set_fp32_math(dad_handle *h, int32_t mode);
 /* How the stride-1 convolutions of the U-Net (temporal_unet.py:106-122, 214-237) are grouped into launches, bf16
  * mode: 3 (default) = one persistent conv_chain launch per run of ResidualTemporalBlocks of one level (their convs
  * synchronise through per-sample-tile counters instead of kernel boundaries), 2 = one launch per block, 1 = one

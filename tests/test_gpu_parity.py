@@ -385,7 +385,8 @@ def test_fp32_ill_conditioned_steps_option(name):
     first_off = helpers.rel_l2(outs[False][1][0].cpu().numpy(), trace[0])
     first_on = helpers.rel_l2(outs[True][1][0].cpu().numpy(), trace[0])
     assert first_on < TOL["bf16"], (first_on, first_off)
-    assert first_on < 0.5 * first_off or first_off < 2e-3
+    # the TF32 sibling: at most half the bf16 error, or already far inside the tolerance
+    assert first_on < max(0.5 * first_off, 0.3 * TOL["bf16"]), (first_on, first_off)
     assert torch.equal(outs[True][1][-1], outs[True][0])
     assert helpers.rel_l2(outs[True][0].cpu().numpy(), trace[-1]) < FREE_TOL["bf16"]
     # Philox path: same split, results finite, conditions exact
