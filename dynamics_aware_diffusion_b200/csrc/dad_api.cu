@@ -120,6 +120,7 @@ struct dad_handle {
   std::string err;
   int sm_count = 0;
   int step_ctas_per_sm = 8;   // resident step_pointwise_kernel CTAs per SM (occupancy query)
+  int step_ctas_per_sm_lean = 8;
   int max_smem_optin = 0;
   bool bf16 = false;
   int time_dim = 0, D = 0, Cpad_in = 0;
@@ -150,6 +151,7 @@ struct dad_handle {
   // The fused SIMT projector (projector in shared memory) wins while the batch is small enough to be latency-bound; from
   // this batch on the tensor-core path (pointwise + bf16x3 GEMM) is used even when the fused kernel fits (measured
   // cross-over, tools/step_times.py).  force_proj_tc: measurement switch of dad_time_step_kernel (flag 0x200).
+  bool step_lean = false;            // the step being enqueued has Philox noise, no gradient, no trace (step_pointwise_kernel<true>)
   int f32_math = 0;                  // dad_set_fp32_math: 0 IEEE fp32 SIMT, 1 TF32 tensor cores, 2 3xTF32
   // dad_set_fp32_steps: reverse steps with index >= fp32_min_step take eps from this fp32 handle
   dad_handle *companion = nullptr;
@@ -929,14 +931,18 @@ int set_kernel_attrs(dad_handle *h) {
 #define T3_ATTR(gw, mh, mode, ns) CK(h, (set_t3_attr<gw, mh, mode, ns>(h->max_smem_optin)));
   T3_FOR_EACH(T3_ATTR)
 #undef T3_ATTR
-#define STEP_ATTR(spt) CK(h, cudaFuncSetAttribute(step_project_fused_kernel<spt>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+#define STEP_ATTR(spt)                                                                                                        \
+  CK(h, cudaFuncSetAttribute(step_project_fused_kernel<spt, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin)); \
+  CK(h, cudaFuncSetAttribute(step_project_fused_kernel<spt, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   STEP_FOR_EACH_SPT(STEP_ATTR)
 #undef STEP_ATTR
 #define SMALL_ATTR(mt, nt) CK(h, cudaFuncSetAttribute(conv_small_kernel<mt, nt>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   SMALL_FOR_EACH(SMALL_ATTR)
 #undef SMALL_ATTR
-  CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->step_ctas_per_sm, step_pointwise_kernel, 256, 0));
+  CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->step_ctas_per_sm, step_pointwise_kernel<false>, 256, 0));
   if (h->step_ctas_per_sm < 1) h->step_ctas_per_sm = 1;
+  CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->step_ctas_per_sm_lean, step_pointwise_kernel<true>, 256, 0));
+  if (h->step_ctas_per_sm_lean < 1) h->step_ctas_per_sm_lean = 1;
   return DAD_OK;
 }
 
@@ -1189,8 +1195,10 @@ int enqueue_step(dad_handle *h, const float *model_out, int B, bool project, boo
   if (total4 >= (size_t)1 << 31) DAD_FAIL(h, DAD_ERR_INVALID, "step kernel: B*H*T/4 must be below 2^31");
   if (!project) {
     p.to_tmp = 0;
-    const int grid = (int)std::min<size_t>(cdiv(total4, 256), (size_t)h->sm_count * h->step_ctas_per_sm);
-    launch_k(step_pointwise_kernel, dim3(grid), dim3(256), 0, st, 1, p);
+    const bool lean = h->step_lean && c.predict_epsilon && c.clip_denoised;
+    const int grid = (int)std::min<size_t>(cdiv(total4, 256), (size_t)h->sm_count * (lean ? h->step_ctas_per_sm_lean : h->step_ctas_per_sm));
+    if (lean) launch_k(step_pointwise_kernel<true>, dim3(grid), dim3(256), 0, st, 1, p);
+    else launch_k(step_pointwise_kernel<false>, dim3(grid), dim3(256), 0, st, 1, p);
     h->counting += 1;
   } else if (h->proj_tc && (!step_fused_fits(h) || B >= h->proj_tc_min_batch || h->force_proj_tc)) {
     // large D (the projector does not fit shared memory): pointwise part -> x' (fp32) + its bf16 (hi | lo | hi) split; then one tcgen05 GEMM against (N_hi | N_hi | N_lo)
@@ -1199,7 +1207,7 @@ int enqueue_step(dad_handle *h, const float *model_out, int B, bool project, boo
     p.split = h->d_split;
     p.Kp = h->projKp;
     const int grid = (int)std::min<size_t>(cdiv(total4, 256), (size_t)h->sm_count * h->step_ctas_per_sm);
-    launch_k(step_pointwise_kernel, dim3(grid), dim3(256), 0, st, 1, p);
+    launch_k(step_pointwise_kernel<false>, dim3(grid), dim3(256), 0, st, 1, p);
     ConvTcParams t{};
     t.bias = h->d_qpad;
     t.ls = h->d_ls;
@@ -1233,8 +1241,13 @@ int enqueue_step(dad_handle *h, const float *model_out, int B, bool project, boo
       const int grid = std::min(cdiv(B, 4 * spt), h->sm_count);
       const dim3 blk(step_fused_threads(h->D));
       const size_t smem = step_fused_smem(h->D);
+      const bool lean = h->step_lean && h->cfg.predict_epsilon && h->cfg.clip_denoised;      // see step_pointwise_kernel<true>
       switch (spt) {
-#define STEP_CASE(c) case c: launch_k(step_project_fused_kernel<c>, dim3(grid), blk, smem, st, 1, p); break;
+#define STEP_CASE(n)                                                                                \
+  case n:                                                                                           \
+    if (lean) launch_k(step_project_fused_kernel<n, true>, dim3(grid), blk, smem, st, 1, p);        \
+    else launch_k(step_project_fused_kernel<n, false>, dim3(grid), blk, smem, st, 1, p);            \
+    break;
         STEP_FOR_EACH_SPT(STEP_CASE)
 #undef STEP_CASE
       }
@@ -1244,7 +1257,7 @@ int enqueue_step(dad_handle *h, const float *model_out, int B, bool project, boo
       // blends, inpaints and writes x (K8).
       p.to_tmp = 1;
       const int grid = (int)std::min<size_t>(cdiv(total4, 256), (size_t)h->sm_count * h->step_ctas_per_sm);
-      launch_k(step_pointwise_kernel, dim3(grid), dim3(256), 0, st, 1, p);
+      launch_k(step_pointwise_kernel<false>, dim3(grid), dim3(256), 0, st, 1, p);
       ConvF32Params g{};
       g.in1 = h->d_xtmp;
       g.w = h->d_Nt;            // Nt[k][d] is exactly the [c][n] weight layout
@@ -1294,7 +1307,7 @@ void drop_graphs(dad_handle *h) {
 constexpr int kStepsPerGraph = 20;
 
 int get_graph(dad_handle *h, int B, bool project, int reps, GraphEntry **out) {
-  const long long key = ((long long)B * 2 + (project ? 1 : 0)) * 64 + reps;
+  const long long key = (((long long)B * 2 + (project ? 1 : 0)) * 64 + reps) * 2 + (h->step_lean ? 1 : 0);
   auto it = h->graphs.find(key);
   if (it != h->graphs.end()) { *out = &it->second; return DAD_OK; }
   cudaGraph_t graph = nullptr;
@@ -1813,6 +1826,9 @@ int dad_sample(dad_handle *h, float *x, const float *noise_seq, uint64_t seed, u
   CK(h, cudaSetDevice(h->cfg.device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t D = h->D;
+  // the loop state this call installs has Philox noise, no gradient and no trace: the lean step kernel applies
+  h->step_lean = !noise_seq && !trace;
+  struct LeanReset { dad_handle *h; ~LeanReset() { h->step_lean = false; } } lean_reset{h};
   for (int c0 = 0; c0 < B; c0 += h->cfg.max_batch) {
     const int Bc = std::min(h->cfg.max_batch, B - c0);
     LoopState ls{};
@@ -2106,7 +2122,10 @@ int dad_sample_profile(dad_handle *h, float *x, uint64_t seed, uint64_t sample_o
     h->launches += 1;
   }
   GraphEntry *ge = nullptr;
-  if ((rc = get_graph(h, B, project, 1, &ge))) return rc;
+  h->step_lean = true;           // Philox noise, no trace: the kernels dad_sample runs for such a loop
+  rc = get_graph(h, B, project, 1, &ge);
+  h->step_lean = false;
+  if (rc) return rc;
   std::vector<cudaEvent_t> ev(n_steps + 1);
   for (auto &e : ev) CK(h, cudaEventCreate(&e));
   CK(h, cudaEventRecord(ev[0], st));
@@ -2329,7 +2348,9 @@ int dad_time_step_kernel(dad_handle *h, int32_t B, int32_t step, uint32_t flags,
   int rc = set_loop_state(h, ls, st);
   if (rc) return rc;
   h->counting = 0;
+  h->step_lean = !injected;          // what dad_sample selects for a loop without injected noise / trace
   rc = time_launches(h, st, iters, ms, [&]() { return enqueue_step(h, h->d_eps, B, project, false, st); });
+  h->step_lean = false;
   h->launches += h->counting;
   h->force_proj_tc = false;
   h->proj_tc_min_batch = saved_min_batch;

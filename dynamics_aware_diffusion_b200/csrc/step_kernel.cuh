@@ -151,24 +151,30 @@ __device__ __forceinline__ StepView step_view(const StepParams &p) {
 struct StepQuad {
   float4 x, m, z, g;
 };
+// LEAN: the common loop configuration fixed at compile time -- epsilon prediction, clipping, in-kernel Philox noise, no
+// guidance gradient (see step_pointwise_kernel<true>); the generic code is predicated on all of these per element.
+template <bool LEAN = false>
 __device__ __forceinline__ void step_load4(const StepParams &p, const StepView &v, size_t e, StepQuad &q) {
   q.x = *reinterpret_cast<const float4 *>(v.x + e);
   q.m = __ldg(reinterpret_cast<const float4 *>(p.model_out + e));
-  if (v.sig != 0.f && v.noise) q.z = __ldg(reinterpret_cast<const float4 *>(v.noise + e));
-  if (v.gvar != 0.f) q.g = __ldg(reinterpret_cast<const float4 *>(v.grad + e));
+  if constexpr (!LEAN) {
+    if (v.sig != 0.f && v.noise) q.z = __ldg(reinterpret_cast<const float4 *>(v.noise + e));
+    if (v.gvar != 0.f) q.g = __ldg(reinterpret_cast<const float4 *>(v.grad + e));
+  }
 }
 
 // The pointwise part for 4 consecutive elements of sample b starting at d0 (loads already issued).
+template <bool LEAN = false>
 __device__ __forceinline__ void step_math4(const StepParams &p, const StepView &v, int b, int d0, const StepQuad &q,
                                            float out[4]) {
   const float xv[4] = {q.x.x, q.x.y, q.x.z, q.x.w}, mv[4] = {q.m.x, q.m.y, q.m.z, q.m.w};
   float zv[4] = {0.f, 0.f, 0.f, 0.f}, gv[4] = {0.f, 0.f, 0.f, 0.f};
   if (v.sig != 0.f) {
-    const float4 z4 = v.noise ? q.z : philox_normal4((unsigned)(d0 >> 2), (unsigned)v.step, v.sample_offset + b, v.seed);
+    const float4 z4 = (!LEAN && v.noise) ? q.z : philox_normal4((unsigned)(d0 >> 2), (unsigned)v.step, v.sample_offset + b, v.seed);
     zv[0] = z4.x; zv[1] = z4.y; zv[2] = z4.z; zv[3] = z4.w;
   }
-  if (v.gvar != 0.f) { gv[0] = q.g.x; gv[1] = q.g.y; gv[2] = q.g.z; gv[3] = q.g.w; }
-  if (p.predict_epsilon && p.clip_denoised && v.gvar == 0.f) {
+  if (!LEAN && v.gvar != 0.f) { gv[0] = q.g.x; gv[1] = q.g.y; gv[2] = q.g.z; gv[3] = q.g.w; }
+  if (LEAN || (p.predict_epsilon && p.clip_denoised && v.gvar == 0.f)) {
     // the usual configuration (epsilon prediction, clipping, no guidance gradient) on packed fp32x2; the same
     // operations in the same order as the general path below, so the results are bit-identical
     const f32x2 cr2 = pk2(v.cr, v.cr), ncrm1 = pk2(-v.crm1, -v.crm1), c12 = pk2(v.c1, v.c1), c22 = pk2(v.c2, v.c2);
@@ -185,6 +191,7 @@ __device__ __forceinline__ void step_math4(const StepParams &p, const StepView &
     }
     return;
   }
+  if constexpr (!LEAN) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     float x0 = p.predict_epsilon ? (v.cr * xv[j] - v.crm1 * mv[j]) : mv[j];
@@ -192,6 +199,7 @@ __device__ __forceinline__ void step_math4(const StepParams &p, const StepView &
     float mu = v.c1 * x0 + v.c2 * xv[j];
     mu += v.gvar * gv[j];
     out[j] = mu + v.sig * zv[j];
+  }
   }
 }
 
@@ -220,14 +228,18 @@ __device__ __forceinline__ void cond_override(const StepParams &p, const StepVie
 #endif
 constexpr int STEP_U = DAD_STEP_U;
 
+// LEAN = true: epsilon prediction + clipping, Philox noise, no guidance gradient, no trace, no projector GEMM behind it
+// (to_tmp / split) -- the host selects it when the loop it enqueues is exactly that (dad_sample without noise_seq /
+// trace; part of the captured graph's key).  Same arithmetic, ~1/4 fewer instructions per float4.
+template <bool LEAN>
 __global__ void __launch_bounds__(256) step_pointwise_kernel(const StepParams p) {
   ptx::griddep_launch();
   ptx::griddep_wait();
   const StepView v = step_view(p);
   // when a projector GEMM follows, inpaint here only in the inpaint -> project order
-  const int n_cond = (!p.to_tmp || (v.flags & 4u)) ? v.n_cond : 0;
-  float *dst = p.to_tmp ? p.xtmp : v.x;
-  float *tr = p.to_tmp ? nullptr : v.trace;
+  const int n_cond = (LEAN || !p.to_tmp || (v.flags & 4u)) ? v.n_cond : 0;
+  float *dst = (!LEAN && p.to_tmp) ? p.xtmp : v.x;
+  float *tr = (LEAN || p.to_tmp) ? nullptr : v.trace;
   // 32-bit quad indices (the host rejects B*D/4 >= 2^31); (sample, offset) of this thread's float4 advance by a
   // fixed stride: one division up front, none in the loop
   const unsigned total4 = (unsigned)((size_t)p.B * p.D / 4);
@@ -239,11 +251,26 @@ __global__ void __launch_bounds__(256) step_pointwise_kernel(const StepParams p)
   // quick reject for inpainting: the first two conditions' element ranges live in registers
   const unsigned span = (unsigned)p.T + 3u;
   const int lo0 = n_cond > 0 ? __ldg(&p.ls->cond_h[0]) * p.T : 0, lo1 = n_cond > 1 ? __ldg(&p.ls->cond_h[1]) * p.T : lo0;
-  while (q4 < total4) {
-    StepQuad q[STEP_U];
+  // LEAN: software-pipelined -- the loads of the NEXT pair of quads are issued before the Philox / Box-Muller work of
+  // the current pair (~140 instructions per quad), so every warp has memory requests in flight while it computes
+  // (without it the Philox variant ran at 0.64-0.70 of the HBM peak with issue slots and pipes half idle).
+  StepQuad q[STEP_U], qn[STEP_U];
+  if constexpr (LEAN) {
 #pragma unroll
     for (int u = 0; u < STEP_U; ++u)
-      if (q4 + u * stride4 < total4) step_load4(p, v, (size_t)(q4 + u * stride4) * 4, q[u]);
+      if (q4 + u * stride4 < total4) step_load4<true>(p, v, (size_t)(q4 + u * stride4) * 4, q[u]);
+  }
+  while (q4 < total4) {
+    if constexpr (LEAN) {
+      const unsigned nx = q4 + STEP_U * stride4;
+#pragma unroll
+      for (int u = 0; u < STEP_U; ++u)
+        if (nx + u * stride4 < total4) step_load4<true>(p, v, (size_t)(nx + u * stride4) * 4, qn[u]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < STEP_U; ++u)
+        if (q4 + u * stride4 < total4) step_load4<false>(p, v, (size_t)(q4 + u * stride4) * 4, q[u]);
+    }
 #pragma unroll
     for (int u = 0; u < STEP_U; ++u) {
       if (q4 < total4) {
@@ -251,13 +278,13 @@ __global__ void __launch_bounds__(256) step_pointwise_kernel(const StepParams p)
         const int b = (int)b_u;
         const int d0 = (int)(d4 * 4u);
         float o[4];
-        step_math4(p, v, b, d0, q[u], o);
+        step_math4<LEAN>(p, v, b, d0, q[u], o);
         if (n_cond && ((unsigned)(d0 - lo0 + 3) < span || (unsigned)(d0 - lo1 + 3) < span || n_cond > 2))
           cond_override<4>(p, v, n_cond, b, d0, o);
         const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
         *reinterpret_cast<float4 *>(dst + e) = o4;
         if (tr) *reinterpret_cast<float4 *>(tr + e) = o4;
-        if (p.split) {
+        if (!LEAN && p.split) {
           // x' = hi + lo with hi, lo in bf16: three bf16 products recover fp32-level accuracy on the tensor cores
           __nv_bfloat16 hi[4], lo[4];
 #pragma unroll
@@ -277,6 +304,10 @@ __global__ void __launch_bounds__(256) step_pointwise_kernel(const StepParams p)
       d4 += sd;
       if (d4 >= D4) { d4 -= D4; b_u += 1; }
     }
+    if constexpr (LEAN) {
+#pragma unroll
+      for (int u = 0; u < STEP_U; ++u) q[u] = qn[u];
+    }
   }
 }
 
@@ -294,7 +325,7 @@ __host__ __device__ constexpr size_t step_fused_smem(int D) {
 }
 __host__ __device__ constexpr int step_fused_threads(int D) { return (4 * D + 31) / 32 * 32; }
 
-template <int SPT>
+template <int SPT, bool LEAN = false>
 __global__ void __launch_bounds__(STEP_FUSED_MAX_THREADS) step_project_fused_kernel(const StepParams p) {
   extern __shared__ __align__(16) float smem[];
   constexpr int SB = 4 * SPT, NP = (SPT + 1) / 2;
@@ -336,7 +367,7 @@ __global__ void __launch_bounds__(STEP_FUSED_MAX_THREADS) step_project_fused_ker
         const int w = w0 + u * blockDim.x;
         s[u] = w / D4;
         d0[u] = (w - s[u] * D4) * 4;
-        if (w < SB * D4 && b0 + s[u] < p.B) step_load4(p, v, (size_t)(b0 + s[u]) * D + d0[u], q[u]);
+        if (w < SB * D4 && b0 + s[u] < p.B) step_load4<LEAN>(p, v, (size_t)(b0 + s[u]) * D + d0[u], q[u]);
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -345,7 +376,7 @@ __global__ void __launch_bounds__(STEP_FUSED_MAX_THREADS) step_project_fused_ker
         const int b = b0 + s[u];
         float o[4] = {0.f, 0.f, 0.f, 0.f};
         if (b < p.B) {
-          step_math4(p, v, b, d0[u], q[u], o);
+          step_math4<LEAN>(p, v, b, d0[u], q[u], o);
           if (inpaint_first && n_cond) cond_override<4>(p, v, n_cond, b, d0[u], o);
         }
         const int qq = s[u] / SPT, sl = s[u] - qq * SPT;
@@ -392,7 +423,7 @@ __global__ void __launch_bounds__(STEP_FUSED_MAX_THREADS) step_project_fused_ker
           float y = xd[s] + alpha * (r[s] + qd);
           if (pc >= 0) y = p.cond_vals[((size_t)pc * v.cond_mul + (v.cond_row >= 0 ? v.cond_row + b : 0)) * p.T + ptt];
           v.x[(size_t)b * D + pd] = y;
-          if (v.trace) v.trace[(size_t)b * D + pd] = y;
+          if (!LEAN && v.trace) v.trace[(size_t)b * D + pd] = y;
         }
       }
     }
