@@ -50,6 +50,9 @@ constexpr int CH_BK = 64;
 #endif
 constexpr int CH_MAX_CONVS = DAD_CH_MAX_CONVS;
 constexpr int CH_MAX_NB = 8;          // weight-tile ring depth (runtime, <= 8)
+#ifndef DAD_CH_EARLY_PUBLISH
+#define DAD_CH_EARLY_PUBLISH 1
+#endif
 
 __host__ __device__ constexpr bool ch_narrow(int gw) { return gw == 16 || gw == 32; }
 // Epilogue shape per GroupNorm width: 16-column TMEM chunks everywhere (8 independent fp32x2 chains per thread and loop
@@ -593,7 +596,15 @@ conv_chain_kernel(const __grid_constant__ ChainArgs args) {
       if (have_next && wt < UC) store_col(pbuf0 + (uint32_t)((k + 1) & 1) * PBUF, ng, ne, nbi, ntv);
       // the staging buffer is free again once the previous store has read it; the elected thread checked that
       // before it prefetched this unit's residual (or checks it here when there is none)
-      if (!has_res && elected) ptx::bulk_wait_read0();
+      if (elected) {
+        if (!has_res) ptx::bulk_wait_read0();
+#if DAD_CH_EARLY_PUBLISH
+        // the previous unit's store was issued a whole pass 1 ago: it has landed, publish it NOW rather than after this
+        // unit's pass 2 -- consumers of that tile (the next conv of the chain, on another cluster) are 3-4 work-list
+        // rounds behind at most, and a late counter makes their producer warps spin (tools/chain_stalls.py)
+        publish_pending();
+#endif
+      }
       if (XWG && !plain) ptx::named_bar_sync(7, 256);      // both halves of the group have their partial sums out
       else ptx::named_bar_sync(1 + wg, 128);               // statistics exchanged, staging buffer reusable
 
