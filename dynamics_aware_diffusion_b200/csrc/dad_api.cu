@@ -1066,7 +1066,7 @@ int enqueue_f32(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
   const bool vec = (op.g.C1 % 4 == 0) && (op.g.C2 % 4 == 0) && (op.g.Cout % 4 == 0);
   dim3 grid(cdiv((long long)B * op.g.L_out, F32_BM), cdiv(op.g.Cout, F32_BN));
   // dad_set_fp32_math: the tensor-core variants take the layers whose channel counts they are written for
-  const bool tf = h->f32_math != 0 && vec && (op.g.Cout % 8 == 0);
+  const bool tf = h->f32_math != 0 && op.g.C1 % 16 == 0 && op.g.C2 % 16 == 0 && op.g.Cout % 8 == 0;
   if (tf && h->f32_math == 2) launch_k(conv_tf32_kernel<true>, grid, dim3(256), 0, st, 1, p);
   else if (tf) launch_k(conv_tf32_kernel<false>, grid, dim3(256), 0, st, 1, p);
   else if (vec) launch_k(conv_f32_kernel<EPI_BIAS, true>, grid, dim3(256), 0, st, 1, p);
@@ -1083,7 +1083,12 @@ int enqueue_f32(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
     q.ls = h->d_ls;
     q.L = op.g.L_out;
     q.C = op.g.Cout;
-    launch_k(gn_mish_f32_kernel, dim3(B, kGroups), dim3(128), 0, st, 1, q);
+    // one warp per (sample, group) with the group in registers when it fits, else one block per (sample, group)
+    const int gw = q.C / kGroups, n4 = q.L * gw / 4, pairs = B * kGroups;
+    if (gw % 4 == 0 && n4 <= 32 * 4) launch_k(gn_mish_f32_warp_kernel<4>, dim3(cdiv(pairs, 8)), dim3(256), 0, st, 1, q, pairs);
+    else if (gw % 4 == 0 && n4 <= 32 * 8) launch_k(gn_mish_f32_warp_kernel<8>, dim3(cdiv(pairs, 8)), dim3(256), 0, st, 1, q, pairs);
+    else if (gw % 4 == 0 && n4 <= 32 * 16) launch_k(gn_mish_f32_warp_kernel<16>, dim3(cdiv(pairs, 8)), dim3(256), 0, st, 1, q, pairs);
+    else launch_k(gn_mish_f32_kernel, dim3(B, kGroups), dim3(128), 0, st, 1, q);
     h->counting += 1;
   }
   return DAD_OK;

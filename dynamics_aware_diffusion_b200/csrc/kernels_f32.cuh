@@ -239,29 +239,28 @@ __global__ void __launch_bounds__(256) conv_tf32_kernel(const ConvF32Params p) {
       for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
 
   float av[8], bv[4];
-  auto load_tile = [&](int k0) {       // channel counts are multiples of 4 here (the host routes the others to the SIMT kernel)
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      float *a4 = av + 4 * q;
-      a4[0] = a4[1] = a4[2] = a4[3] = 0.f;
-      const int kk = k0 + a_k + 4 * q;
-      if (a_ok && kk < K) {
-        const int tap = kk / Cin, c = kk - tap * Cin;
-        const int li = alo * g.in_stride + g.tap_off[tap];
-        if (li >= 0 && li < g.L_in) {
-          const float *src = (c < g.C1) ? p.in1 + ((size_t)(ab * g.L_in + li) * g.C1 + c)
-                                        : p.in2 + ((size_t)(ab * g.L_in + li) * g.C2 + (c - g.C1));
-          const float4 v = *reinterpret_cast<const float4 *>(src);
-          a4[0] = v.x; a4[1] = v.y; a4[2] = v.z; a4[3] = v.w;
-        }
-      }
+  // Channel counts are multiples of 16 here (the host routes the others to the SIMT kernel), so a 16-wide k block lies
+  // inside one tap and one source: (tap, channel) of the block advance incrementally, no division in the loop.
+  int l_tap = 0, l_c = 0;                 // tap and first channel of the k block load_tile fetches next
+  const float *b_src = p.w + (size_t)b_k * g.Cout + n0 + b_n;
+  const bool b_ok = n0 + b_n + 3 < g.Cout;
+  auto load_tile = [&](int k0) {
+    const int li = alo * g.in_stride + g.tap_off[l_tap];
+    const bool ok = a_ok && k0 < K && li >= 0 && li < g.L_in;
+    const int c = l_c + a_k;
+    const float *src = (c < g.C1) ? p.in1 + ((size_t)(ab * g.L_in + li) * g.C1 + c)
+                                  : p.in2 + ((size_t)(ab * g.L_in + li) * g.C2 + (c - g.C1));
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, vb4 = v0;
+    if (ok) {
+      v0 = *reinterpret_cast<const float4 *>(src);
+      v1 = *reinterpret_cast<const float4 *>(src + 4);
     }
-    bv[0] = bv[1] = bv[2] = bv[3] = 0.f;
-    const int kk = k0 + b_k, n = n0 + b_n;
-    if (kk < K && n + 3 < g.Cout) {
-      const float4 v = *reinterpret_cast<const float4 *>(p.w + (size_t)kk * g.Cout + n);
-      bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
-    }
+    if (b_ok && k0 < K) vb4 = *reinterpret_cast<const float4 *>(b_src + (size_t)k0 * g.Cout);
+    av[0] = v0.x; av[1] = v0.y; av[2] = v0.z; av[3] = v0.w;
+    av[4] = v1.x; av[5] = v1.y; av[6] = v1.z; av[7] = v1.w;
+    bv[0] = vb4.x; bv[1] = vb4.y; bv[2] = vb4.z; bv[3] = vb4.w;
+    l_c += F32_BK;
+    if (l_c >= Cin) { l_c = 0; ++l_tap; }
   };
   auto rnd = [](float x) -> float { return X3 ? x : __uint_as_float(cvt_tf32_rn(x)); };
   auto store_tile = [&](int buf) {
@@ -409,6 +408,70 @@ __global__ void __launch_bounds__(128) gn_mish_f32_kernel(const GnF32Params p) {
     if (p.ttab) v += p.ttab[(size_t)t * p.C + c];
     if (p.residual) v += p.residual[idx];
     p.out[idx] = v;
+  }
+}
+
+// The same operation with ONE WARP per (sample, group) and the group's L x gw elements held in registers (NV float4 per
+// lane): one read, one write, no block barriers, no per-element division in the passes.  Used whenever the group fits
+// (L * gw <= 128 * NV; every layer of the PointMaze / HalfCheetah / Door U-Nets at H = 32); two-pass variance as above.
+template <int NV>
+__global__ void __launch_bounds__(256) gn_mish_f32_warp_kernel(const GnF32Params p, int n_pairs) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
+  const int lane = threadIdx.x & 31;
+  const int pair = blockIdx.x * 8 + (threadIdx.x >> 5);        // (sample, group) index
+  if (pair >= n_pairs) return;
+  const int b = pair / kGroups, grp = pair - b * kGroups;
+  const int gw = p.C / kGroups, g4 = gw >> 2;                  // gw is a multiple of 4 here
+  const int n4 = p.L * g4;
+  const size_t base = (size_t)b * p.L * p.C + (size_t)grp * gw;
+  float4 v[NV];
+  size_t off[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e4 = lane + 32 * i;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    off[i] = 0;
+    if (e4 < n4) {
+      const int l = e4 / g4, j = (e4 - l * g4) * 4;
+      off[i] = base + (size_t)l * p.C + j;
+      v[i] = *reinterpret_cast<const float4 *>(p.in + off[i]);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float n = (float)(p.L * gw);
+  const float mean = warp_sum(s) / n;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if (lane + 32 * i < n4) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / n + kGnEps);
+  long long t = 0;
+  if (p.ttab) t = p.ls->t_rows ? min(max(p.ls->t_rows[b], 0ll), (long long)p.ls->n_table - 1) : (long long)p.ls->step;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e4 = lane + 32 * i;
+    if (e4 >= n4) continue;
+    const int l = e4 / g4, c = grp * gw + (e4 - l * g4) * 4;
+    const float4 ga = *reinterpret_cast<const float4 *>(p.gamma + c), be = *reinterpret_cast<const float4 *>(p.beta + c);
+    float4 o;
+    o.x = mish_precise((v[i].x - mean) * rstd * ga.x + be.x);
+    o.y = mish_precise((v[i].y - mean) * rstd * ga.y + be.y);
+    o.z = mish_precise((v[i].z - mean) * rstd * ga.z + be.z);
+    o.w = mish_precise((v[i].w - mean) * rstd * ga.w + be.w);
+    if (p.ttab) {
+      const float4 tt = *reinterpret_cast<const float4 *>(p.ttab + (size_t)t * p.C + c);
+      o.x += tt.x; o.y += tt.y; o.z += tt.z; o.w += tt.w;
+    }
+    if (p.residual) {
+      const float4 r = *reinterpret_cast<const float4 *>(p.residual + off[i]);
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    *reinterpret_cast<float4 *>(p.out + off[i]) = o;
   }
 }
 
