@@ -349,3 +349,84 @@ def test_weight_writes_through_data_are_seen():
     with pytest.raises(ValueError):
         dif.model(x, torch.full((4,), 2.5, device=_dev()))
     assert torch.equal(dif.model(x, torch.full((4,), 3.0, device=_dev())), dif.model(x, t))
+
+
+def test_lean_step_kernel_equals_generic_kernel():
+    """dad_sample without injected noise / trace takes the LEAN instantiations of the step kernels (loop configuration fixed
+    at compile time, software-pipelined loads); with a trace it takes the generic ones.  Same Philox draws, same
+    arithmetic: identical bits, for the plain policy (step_pointwise_kernel) and the dynamics-aware one (fused projector)."""
+    from dynamics_aware_diffusion_b200 import (TemporalUnet, GaussianDiffusion, GuidedPolicy, DynamicsAwarePolicy,
+                                               ProjectionMatrixBuilder, synthetic)
+    net = TemporalUnet(6, dim=64, dim_mults=(1, 2), precision="bf16", max_batch=512)
+    dif = GaussianDiffusion(net, horizon=32, observation_dim=4, action_dim=2, n_timesteps=8)
+    synthetic.fill_state_dict(dif, 2)
+    dif.to(_dev())
+    nz = synthetic.SyntheticNormalizer(4, 2)
+    A, Bm = synthetic.double_integrator(0.1)
+    P = ProjectionMatrixBuilder(A, Bm, 4, 2).get_projection_matrix(32)
+    start = torch.zeros(1, 6, device=_dev())
+    start[0, :4] = torch.tensor([0.1, 0.2, -0.3, 0.0])
+    for pol in (GuidedPolicy(dif, nz),
+                DynamicsAwarePolicy(dif, projection_matrix=P, normalizer=nz, state_dim=4, observation_dim=4, action_dim=2,
+                                    horizon=32, projection_schedule="noise_schedule")):
+        for B in (3, 300):
+            torch.manual_seed(3)
+            lean = pol.sample_loop(batch_size=B, conditions={0: start}, seed=17)
+            torch.manual_seed(3)
+            generic, trace = pol.sample_loop(batch_size=B, conditions={0: start}, seed=17, return_trace=True)
+            assert torch.equal(lean, generic), type(pol).__name__
+            assert torch.equal(trace[-1], generic)
+
+
+def test_tensor_core_projector_for_large_batches_matches_the_fused_kernel(pointmaze_full):
+    """From B >= 8192 the D = 192 projector runs on the tensor cores (pointwise kernel + bf16x3 tcgen05 GEMM) instead of
+    the fused SIMT kernel.  A plan's result does not depend on its batch (Philox subsequence = global index), so rows of a
+    B = 8192 loop must equal the same rows sampled in a small batch up to the bf16x3 rounding of the projector
+    (fp32-level: 3 bf16 products)."""
+    dif, pol, P, nz = pointmaze_full
+    from dynamics_aware_diffusion_b200 import TemporalUnet, GaussianDiffusion, DynamicsAwarePolicy, synthetic
+    net = TemporalUnet(6, dim=128, dim_mults=(1, 2, 4), precision="bf16", max_batch=8192, latency_max_batch=0)
+    dif2 = GaussianDiffusion(net, horizon=32, observation_dim=4, action_dim=2, n_timesteps=6, beta_schedule="linear")
+    synthetic.fill_state_dict(dif2, 0)
+    dif2.to(_dev())
+    pol2 = DynamicsAwarePolicy(dif2, projection_matrix=P, normalizer=nz, state_dim=4, observation_dim=4, action_dim=2,
+                               horizon=32, projection_schedule="noise_schedule", projection_strength=1.0)
+    start = torch.zeros(1, 6, device=_dev())
+    start[0, :4] = torch.tensor([0.3, -0.2, 0.1, 0.0])
+    big = pol2.sample_loop(batch_size=8192, conditions={0: start}, seed=5)
+    small = pol2.sample_loop(batch_size=64, conditions={0: start}, seed=5, sample_offset=4000)
+    assert bool(torch.isfinite(big).all()) and bool((big[:, 0] == start).all())
+    err = helpers.rel_l2(big[4000:4064].cpu().numpy(), small.cpu().numpy())
+    assert 0 < err < 2e-4, err          # not bit-equal (another projector path), equal to fp32-level accuracy
+    del pol2, dif2, net
+    torch.cuda.empty_cache()
+
+
+def test_fp32_sibling_api_and_math_modes():
+    """dad_set_fp32_steps / dad_set_fp32_math through the raw C ABI: argument validation, and the accuracy ordering of the
+    sibling's arithmetic (TF32 tensor cores < 2e-3, 3xTF32 < 5e-5, IEEE fp32 < 1e-5 on eps vs the reference)."""
+    import ctypes
+    from dynamics_aware_diffusion_b200 import _native as N
+    import test_gpu_parity as T
+    c, g, dif, sd = T.models("pointmaze", "bf16")
+    eng = dif.engine(c["H"], _dev())
+    comp = eng._companion
+    assert comp is not None and comp[1] == c["S"] - 1 and comp[0].precision == "fp32"
+    L = N.lib()
+    assert L.dad_set_fp32_steps(eng.handle, eng.handle, 0) == N.ERR_INVALID          # a bf16 handle is no fp32 companion
+    assert L.dad_set_fp32_steps(comp[0].handle, comp[0].handle, 0) == N.ERR_INVALID  # nor is a handle its own
+    assert L.dad_set_fp32_math(eng.handle, 1) == N.ERR_INVALID                       # bf16 handles have no fp32 math mode
+    assert L.dad_set_fp32_math(comp[0].handle, 7) == N.ERR_INVALID
+    x = T.cu(g["x_init"])
+    k = list(g["unet_steps"]).index(c["S"] - 1)
+    errs = {}
+    for mode in ("tf32", "tf32x3", "fp32"):
+        comp[0].set_fp32_math(mode)
+        errs[mode] = helpers.rel_l2(comp[0].unet_forward(x, step=c["S"] - 1).cpu().numpy(), g["unet_eps"][k])
+    comp[0].set_fp32_math(dif.ill_conditioned_math)
+    assert errs["tf32"] < 2e-3 and errs["tf32x3"] < 5e-5 and errs["fp32"] < 1e-5, errs
+    # detaching restores the all-bf16 loop; re-attaching through engine() restores the default
+    dif.fp32_ill_conditioned_steps = False
+    assert dif.engine(c["H"], _dev())._companion is None
+    dif.fp32_ill_conditioned_steps = True
+    assert dif.engine(c["H"], _dev())._companion is not None
