@@ -10,6 +10,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <map>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -34,6 +35,11 @@ using namespace dad;
 namespace {
 
 thread_local std::string g_create_error;
+// Live handles, so that destroying an fp32 companion detaches it from every handle that still points at it
+// (dad_set_fp32_steps) instead of leaving a dangling pointer.
+static std::mutex g_handles_mutex;
+static std::vector<dad_handle *> g_handles;
+
 
 struct Act {
   size_t off;     // byte offset per sample
@@ -1517,12 +1523,22 @@ int dad_create(const dad_config *cfg, dad_handle **out) {
   }
   if ((rc = build_units(h))) return fail(rc);
   if (cudaDeviceSynchronize() != cudaSuccess) { h->err = "device error during create"; return fail(DAD_ERR_CUDA); }
+  {
+    std::lock_guard<std::mutex> lock(g_handles_mutex);
+    g_handles.push_back(h);
+  }
   *out = h;
   return DAD_OK;
 }
 
 int dad_destroy(dad_handle *h) {
   if (!h) return DAD_OK;
+  {
+    std::lock_guard<std::mutex> lock(g_handles_mutex);
+    g_handles.erase(std::remove(g_handles.begin(), g_handles.end(), h), g_handles.end());
+    for (dad_handle *o : g_handles)
+      if (o->companion == h) { o->companion = nullptr; o->fp32_min_step = INT_MAX; }
+  }
   cudaDeviceSynchronize();
   drop_graphs(h);
   for (void *p : h->allocs) cudaFree(p);
