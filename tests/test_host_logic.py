@@ -225,3 +225,56 @@ def test_optional_knobs_do_not_change_the_reference_surface():
         # the device build needs a GPU and says so through the C-ABI error channel
         with pytest.raises(_native.DadError):
             b.get_projection_matrix(16, device="cuda:0")
+
+
+def test_ill_conditioned_step_detection_is_index_based():
+    """GaussianDiffusion.ill_conditioned_min_step: the trailing run of step indices with d(mean)/d(eps) > 10 -- index S-1
+    only for the cosine schedule (beta clipped to 0.9999, diffusion.py:41), none for the linear one; a shortened loop
+    (n_timesteps lowered after construction, evaluate.py:351-353) never reaches it."""
+    from dynamics_aware_diffusion_b200 import TemporalUnet, GaussianDiffusion
+    net = TemporalUnet(6, dim=32, dim_mults=(1, 2))
+    cos = GaussianDiffusion(net, horizon=16, observation_dim=4, action_dim=2, n_timesteps=100, beta_schedule="cosine")
+    assert cos.fp32_ill_conditioned_steps is True and cos.ill_conditioned_math == "tf32"
+    assert cos.ill_conditioned_min_step() == 99 and cos.ill_conditioned_prefix() == 1
+    assert cos.ill_conditioned_prefix(50) == 0
+    amp = (cos.posterior_mean_coef1 * cos.sqrt_recipm1_alphas_cumprod)
+    assert float(amp[99]) > 10.0 and float(amp[:99].max()) < 1.5
+    lin = GaussianDiffusion(net, horizon=16, observation_dim=4, action_dim=2, n_timesteps=100, beta_schedule="linear")
+    assert lin.ill_conditioned_min_step() == 100 and lin.ill_conditioned_prefix() == 0
+
+
+def test_bench_arms_share_one_config_object():
+    """bench.py: the b200 arm and the reference arm print the SAME `config` (workload_config), for every N and scaling."""
+    import bench
+    w = bench.WORKLOADS["pointmaze"]
+    for world, scaling in ((1, "strong"), (8, "strong"), (8, "weak")):
+        c = bench.workload_config("pointmaze", w, world, scaling)
+        assert c["B_total"] == (4096 if scaling == "strong" else 4096 * world) and c["B_per_gpu"] * world == c["B_total"]
+        assert c["diffusion_steps"] == 500 and c["H"] == 32 and c["T"] == 6 and c["policy"] == "dynamics-aware"
+        assert "model" not in c
+    assert bench.workload_config("pointmaze_guided", bench.WORKLOADS["pointmaze_guided"], 1, "strong")["policy"] == "guided"
+
+
+def test_launch_share_tool_separates_the_sibling_step(tmp_path):
+    """tools/launch_shares.py: one regular diffusion step (conv_chain launches) and the ill-conditioned step of the fp32
+    sibling are reported separately from an ncu launch list."""
+    import subprocess
+    import sys as _sys
+    rows = ['"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size","Device","CC","Section Name","Metric Name","Metric Unit","Metric Value"']
+    seq = (["dad::stage_x_kernel(LoopState *)", "void dad::conv_tf32_kernel<0>(ConvF32Params)", "dad::gn_mish_f32_kernel(GnF32Params)",
+            "void dad::step_project_fused_kernel<7, 1>(StepParams)"] +
+           ["dad::stage_x_kernel(LoopState *)", "void dad::conv_chain_kernel<64, 1, 2>(ChainArgs)",
+            "void dad::conv_tc_kernel<128, 0>(CUtensorMap_st)", "void dad::step_project_fused_kernel<7, 1>(StepParams)"] * 2)
+    for i, name in enumerate(seq):
+        rows.append('"%d","1","python","box","%s","1","7","(256, 1, 1)","(148, 1, 1)","0","10.0","Command line profiler metrics","gpu__time_duration.sum","ns","%d"'
+                    % (i, name, 1000 * (i + 1)))
+    src = tmp_path / "launches.csv"
+    src.write_text("\n".join(rows) + "\n")
+    dst = tmp_path / "shares.md"
+    out = subprocess.run([_sys.executable, os.path.join(helpers.ROOT, "tools", "launch_shares.py"), str(src), str(dst), "cmd"],
+                         capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    text = dst.read_text()
+    assert "regular diffusion step" in text and "conv_chain_kernel<64, 1, 2>" in text
+    assert "ill-conditioned leading step" in text and "conv_tf32_kernel<0>" in text
+    assert text.index("conv_chain_kernel") < text.index("conv_tf32_kernel")
