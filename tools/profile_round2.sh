@@ -19,6 +19,9 @@ ncu -i /tmp/r02_chain.ncu-rep --page source --csv --kernel-id :::3 > /tmp/src3.c
 timeout 200 python tools/step_times.py 262144 > $O/r02_stream.log 2>&1
 timeout 400 ncu --set full --clock-control none -k regex:"step_pointwise" -s 30 -c 1 -f -o /tmp/r02_stream_inj python tools/step_times.py 262144 > $O/r02_ncu4.log 2>&1
 python tools/summarize_ncu.py --out $O r02 stream_b262144 step_pointwise_kernel /tmp/r02_stream_inj.ncu-rep > /dev/null
+# the same kernel with in-kernel Philox noise (the LEAN, software-pipelined instantiation): first launches of step_times.py
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"step_pointwise" -s 5 -c 1 -f -o /tmp/r02_stream_philox python tools/step_times.py 262144 > $O/r02_ncu4b.log 2>&1
+python tools/summarize_ncu.py --out $O r02 stream_philox_b262144 step_pointwise_kernel /tmp/r02_stream_philox.ncu-rep > /dev/null
 # HalfCheetah: the GroupNorm-width-256 chain (9 convs, C_out 2048)
 cat > /tmp/prof_hc.py <<'PY'
 import sys, torch
