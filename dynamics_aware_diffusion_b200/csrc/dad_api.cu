@@ -874,6 +874,11 @@ int build_units(dad_handle *h) {
   return DAD_OK;
 }
 
+// Measured (tools/fusion_sweep.py, PointMaze): with 2 (= 128-wide items whenever a conv's 256-wide items fit in ONE round
+// of the clusters) B = 1024 steps in 0.46 instead of 0.52 ms, B = 2048 / 4096 are unchanged (their convs have 1.7 / 3.5
+// rounds of 256-wide items and keep them); with 4 the B = 2048 / 4096 chains lose 2-5 %.
+constexpr int kChainAltHalfRoundsNarrow = 2, kChainAltHalfRoundsWide = 2;
+
 int enqueue_chain(dad_handle *h, ChainUnit &cu, int B, cudaStream_t st, int flag_epoch = 1) {
   ChainParams &p = cu.args.p;
   p.B = B;
@@ -881,10 +886,13 @@ int enqueue_chain(dad_handle *h, ChainUnit &cu, int B, cudaStream_t st, int flag
   p.flag_epoch = flag_epoch;
   const int cout = h->ops[cu.ops[0]].g.Cout;
   // 256-wide items are the efficient shape (1,610 vs ~1,100 TFLOP/s of MMA issue) when there are rounds of them; when
-  // ALL of a conv's 256-wide items would occupy at most half of the clusters, 128-wide items put twice the clusters to
-  // work and halve the MMA time on every item's critical path
+  // ALL of a conv's 256-wide items fit in one round of the clusters, 128-wide items put twice the clusters to work (or
+  // double the distance, in work-list rounds, between a conv and the conv that consumes it) and halve the MMA time on
+  // every item's critical path
   const int items2 = cdiv(p.n_mst, 2) * (cout / (CH_BN * cu.NS));
-  const bool alt = cu.has_alt && 2 * items2 <= cu.alt_max_clusters;
+  // kChainAltHalfRounds = how many HALF rounds of 256-wide items per conv still take 128-wide items (1 = the rule above)
+  const int alt_r = cu.GW <= 32 ? tuning_env("DAD_CH_ALT_R_NARROW", kChainAltHalfRoundsNarrow) : tuning_env("DAD_CH_ALT_R_WIDE", kChainAltHalfRoundsWide);
+  const bool alt = cu.has_alt && 2 * items2 <= cu.alt_max_clusters * alt_r;
   const int ns = alt ? 1 : cu.NS;
   p.n_tiles_n = cout / (CH_BN * ns);
   p.w_alt = alt ? 1 : 0;
