@@ -371,6 +371,64 @@ def sharded_leg(name, dev, pk, world, dist, B_total, dsteps=10):
             "unet_tensor_frac_of_sustained_per_gpu": out["unet_tensor_frac_of_sustained"] * out["p50_step_latency_ms"] / p50}
 
 
+def config1_full_leg(dev, with_cpu=True):
+    """BASELINE.json configs[0] -- PointMaze guided sampling, B=64, H=32, 100 steps: the reference's own CPU-runnable case --
+    run IN FULL on both sides, nothing extrapolated: `GuidedPolicy.sample_loop(batch_size=64, conditions)` of this package on
+    the GPU (median of 5 loops after 2 warm-up loops, wall clock around the call incl. the final synchronize) and the
+    reference's own `GuidedPolicy.sample_loop` (oracle/_ref, else the torch port) on the host cores (1 loop)."""
+    import contextlib
+    import io
+    import torch
+    from oracle import ref_shim, torch_port
+    from dynamics_aware_diffusion_b200 import GuidedPolicy
+    w = WORKLOADS["pointmaze_guided"]
+    B, S, H, T = w["B"], w["S"], w["H"], w["n"] + w["m"]
+    net, dif = build_policy(w, B, "bf16", dev)
+    _, nz = projector_inputs(w)
+    pol = GuidedPolicy(dif, nz)
+    start = torch.zeros(1, T, device=dev)
+    start[0, :w["n"]] = torch.randn(w["n"], generator=torch.Generator().manual_seed(1234)).to(dev)
+    lat = []
+    for k in range(7):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        x = pol.sample_loop(batch_size=B, conditions={0: start}, seed=k)
+        torch.cuda.synchronize()
+        lat.append(time.perf_counter() - t0)
+    assert bool(torch.isfinite(x).all()) and bool((x[:, 0] == start).all())
+    gpu_s = statistics.median(lat[2:])
+    out = {"workload": "pointmaze_guided", "B": B, "H": H, "T": T, "diffusion_steps": S, "extrapolated": False,
+           "gpu": {"loop_ms": gpu_s * 1e3, "plans_per_s": B / gpu_s, "ms_per_diffusion_step": gpu_s * 1e3 / S}}
+    if with_cpu:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sd = {k: v.detach().cpu() for k, v in dif.state_dict().items()}
+        g = torch.Generator().manual_seed(7)
+        kind = "reference" if ref_shim.available() else "port"
+        if kind == "reference":
+            ref = ref_shim.load()
+            rnet = ref.TemporalUnet(T, dim=w["dim"], dim_mults=w["mults"])
+            rdif = ref.GaussianDiffusion(rnet, horizon=H, observation_dim=w["n"], action_dim=w["m"], n_timesteps=S)
+            rdif.load_state_dict(sd, strict=True)
+            rdif.eval()
+            with contextlib.redirect_stdout(io.StringIO()):
+                rpol = ref.GuidedPolicy(rdif, nz)
+            fn = lambda: rpol.sample_loop(batch_size=B, conditions={0: start.cpu()})
+        else:
+            fn = lambda: torch_port.sample_loop(sd, torch.randn(B, H, T, generator=g),
+                                                lambda k: torch.randn(B, H, T, generator=g), {0: start.cpu()[0]}, None)
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            y = fn()
+            cpu_s = time.perf_counter() - t0
+        assert bool(torch.isfinite(torch.as_tensor(y)).all())
+        out["cpu_reference"] = {"loop_ms": cpu_s * 1e3, "plans_per_s": B / cpu_s, "cores": cores, "kind": kind}
+        out["gpu_over_cpu_reference"] = cpu_s / gpu_s
+    del pol, dif, net
+    torch.cuda.empty_cache()
+    return out
+
+
 def gpu_eager_baseline(w, dev, B, dsteps=3):
     """The honest GPU comparator: the reference's op sequence in STOCK PyTorch eager
     (oracle/torch_port.py: cuDNN convs, native GroupNorm / Mish, the 15-op projection chain, torch.randn noise) on the
@@ -691,6 +749,10 @@ def main():
                     ("pointmaze", {"H": 64}), ("pointmaze", {"H": 128, "B": 2048}),
                     ("pointmaze", {"B": 256}), ("pointmaze", {"B": 1024}), ("pointmaze", {"B": 16384, "max_batch": 16384}),
                     ("pointmaze", {"B": 65536, "max_batch": 16384})]
+            try:
+                line["config1_full"] = config1_full_leg(dev, with_cpu=not args.no_cpu_baseline)
+            except Exception as exc:
+                line["config1_full"] = {"error": str(exc)[:300]}
             line["configs"] = []
             for name, ov in legs:
                 try:
