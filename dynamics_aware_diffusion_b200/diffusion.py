@@ -116,14 +116,15 @@ class GaussianDiffusion(nn.Module):
         self.model._diffusion_cfg = dict(predict_epsilon=bool(self.predict_epsilon), clip_denoised=bool(self.clip_denoised))
         self.model._n_timesteps = int(self.betas.shape[0])
         eng, ent = self.model.engine(horizon or self.horizon, device, n_timesteps=self.betas.shape[0], precision=precision)
-        tag = (id(self), self._schedule_version())
+        ver = self._schedule_version()
+        tag = (id(self), ver)
         if ent.get("schedule_owner") != tag:
             eng.set_schedule(self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod,
                              self.posterior_mean_coef1, self.posterior_mean_coef2, self.posterior_log_variance_clipped)
             ent["schedule_owner"] = tag
         if eng.precision == "bf16":
             # the fp32 sibling for the ill-conditioned steps (dad_set_fp32_steps): same weights, same schedule
-            first = self.ill_conditioned_min_step() if self.fp32_ill_conditioned_steps else int(self.betas.shape[0])
+            first = self.ill_conditioned_min_step(ver) if self.fp32_ill_conditioned_steps else int(self.betas.shape[0])
             if first < int(self.betas.shape[0]):
                 eng32 = self.engine(horizon, device, precision="fp32")
                 if eng32.fp32_math != self.ill_conditioned_math:
@@ -140,11 +141,11 @@ class GaussianDiffusion(nn.Module):
         comp = eng._companion
         return comp[0] if (comp is not None and int(step) >= comp[1]) else eng
 
-    def ill_conditioned_min_step(self) -> int:
+    def ill_conditioned_min_step(self, _version=None) -> int:
         """First index of the TRAILING run of step indices that amplify an eps error by more than 10x:
         d(mean)/d(eps) = posterior_mean_coef1[i] * sqrt_recipm1_alphas_cumprod[i].  len - 1 for the cosine schedule,
         len (none) for the linear one."""
-        tag = self._schedule_version()
+        tag = _version if _version is not None else self._schedule_version()
         if self._ill_cache is None or self._ill_cache[0] != tag:
             amp = (self.posterior_mean_coef1 * self.sqrt_recipm1_alphas_cumprod).detach().cpu()
             i = int(amp.shape[0])
