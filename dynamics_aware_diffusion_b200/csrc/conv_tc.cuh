@@ -101,11 +101,16 @@ __device__ __forceinline__ float mish_tc(float y) {
 }
 
 // GW = GroupNorm group width in columns (0: no GroupNorm/Mish, plain bias epilogue).
-template <int BN, int GW>
+// TF32 = true: the fp32 SIBLING of a bf16 model (dad_set_fp32_steps / dad_set_fp32_math 1) -- activations and weights are
+// fp32 words in global and shared memory (a 128-byte swizzle row holds 32 of them: k blocks of 32 channels), the MMAs are
+// kind::tf32 (K = 8 per instruction, the same 32-byte descriptor advance), the residual is read and the output written
+// as fp32, rounded to TF32 with round-to-nearest (the tensor core would otherwise truncate the next layer's operands).
+template <int BN, int GW, bool TF32 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmW, const ConvTcParams p) {
   using Cfg = TcCfg<BN>;
+  constexpr int BKE = TF32 ? 32 : TC_BK;         // elements per k block = one 128 B swizzle row
   constexpr int CW = (BN < 32) ? 16 : DAD_TC_CW;       // columns per TMEM load
   constexpr int NCHUNK = BN / CW;
   constexpr int NG = (GW > 0) ? BN / GW : 1;    // groups per N-tile
@@ -152,7 +157,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       // the weights are constants: fetch this CTA's whole N tile now, while the previous kernel is still running
       const int n0 = ((int)blockIdx.x % p.n_tiles_n) * BN;
       ptx::mbar_arrive_expect_tx(wfull_bar, (uint32_t)num_kb * Cfg::B_BYTES);
-      for (int kb = 0; kb < num_kb; ++kb) ptx::tma_load_2d(w_res + kb * Cfg::B_ALLOC, &tmW, wfull_bar, kb * TC_BK, n0);
+      for (int kb = 0; kb < num_kb; ++kb) ptx::tma_load_2d(w_res + kb * Cfg::B_ALLOC, &tmW, wfull_bar, kb * BKE, n0);
     }
   }
   if (warp == 1) {
@@ -195,9 +200,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           uint8_t *sa = smem + stage * a_stride;
           uint8_t *sb = sa + Cfg::A_BYTES;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], ws ? Cfg::A_BYTES : Cfg::A_BYTES + Cfg::B_BYTES);
-          if (ch < p.kch1) ptx::tma_load_4d(sa, &tmA1, &full_bar[stage], ch * TC_BK, p.tap_p[tap], p.tap_j[tap], b0);
-          else ptx::tma_load_4d(sa, &tmA2, &full_bar[stage], (ch - p.kch1) * TC_BK, p.tap_p[tap], p.tap_j[tap], b0);
-          if (!ws) ptx::tma_load_2d(sb, &tmW, &full_bar[stage], kb * TC_BK, n0);
+          if (ch < p.kch1) ptx::tma_load_4d(sa, &tmA1, &full_bar[stage], ch * BKE, p.tap_p[tap], p.tap_j[tap], b0);
+          else ptx::tma_load_4d(sa, &tmA2, &full_bar[stage], (ch - p.kch1) * BKE, p.tap_p[tap], p.tap_j[tap], b0);
+          if (!ws) ptx::tma_load_2d(sb, &tmW, &full_bar[stage], kb * BKE, n0);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -206,7 +211,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(TC_BM, BN);
+      constexpr uint32_t idesc = TF32 ? ptx::make_idesc_tf32(TC_BM, BN) : ptx::make_idesc_bf16(TC_BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -225,8 +230,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           const uint64_t db = ptx::make_smem_desc_sw128(ws ? ptx::smem_u32(w_res + kb * Cfg::B_ALLOC) : sa + Cfg::A_BYTES);
 #pragma unroll
           for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-            // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in 16 B units
-            ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            // advance 16 bf16 (8 tf32) = 32 B along K inside the swizzle row: +2 in 16 B units
+            if constexpr (TF32) ptx::umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            else ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
           ptx::umma_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -283,7 +289,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const uint32_t t_addr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
       const size_t orow = ((size_t)b * L_total + (size_t)l * p.out_mul + p.out_phase) * p.Cout + n0;
       // residual of the first column chunk: requested before the accumulator is even ready
-      const bool has_res = (p.residual != nullptr) && valid && !p.out_f32 && !(DAD_DEBUG_BITS(p) & 8);
+      const bool has_res = !TF32 && (p.residual != nullptr) && valid && !p.out_f32 && !(DAD_DEBUG_BITS(p) & 8);
       uint4 rcur[CW / 8];
       if (has_res) {
         const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + orow);
@@ -475,6 +481,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                   o[j] = y[j];
                   if (tr) tr[j] = y[j];
                 }
+            }
+          } else if constexpr (TF32) {
+            // fp32 activations (channel counts are multiples of 64 here): + fp32 residual, round to TF32, 128-bit stores
+            float *o = reinterpret_cast<float *>(p.out) + orow + c * CW;
+            const float *rs = p.residual ? reinterpret_cast<const float *>(p.residual) + orow + c * CW : nullptr;
+#pragma unroll
+            for (int j = 0; j < CW; j += 4) {
+              float4 v = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+              if (rs) {
+                const float4 r4 = __ldg(reinterpret_cast<const float4 *>(rs + j));
+                v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+              }
+              uint32_t t0, t1, t2, t3;
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t0) : "f"(v.x));
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t1) : "f"(v.y));
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t2) : "f"(v.z));
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t3) : "f"(v.w));
+              *reinterpret_cast<uint4 *>(o + j) = make_uint4(t0, t1, t2, t3);
             }
           } else if (p.out_f32) {
             float *o = reinterpret_cast<float *>(p.out) + orow + c * CW;

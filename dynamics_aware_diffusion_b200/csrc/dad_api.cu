@@ -59,6 +59,10 @@ struct ConvOp {
   // device data
   float *w_f32 = nullptr;
   __nv_bfloat16 *w_b16 = nullptr;
+  // fp32 handles: K-major fp32 weights (TF32-rounded) for the tcgen05 kind::tf32 path (BN / GW / tcp / tmA1 / tmA2 / tmW
+  // below then describe THAT launch), see setup_tc32_op
+  float *w_k32 = nullptr;
+  bool tc32 = false;
   float *bias = nullptr, *gamma = nullptr, *beta = nullptr;
   // bf16 path
   int BN = 0, GW = 0;
@@ -515,6 +519,85 @@ int finish_tc_op(dad_handle *h, ConvOp &op) {
   return DAD_OK;
 }
 
+// ---- TF32 tensor-core path of an fp32-precision handle (dad_set_fp32_math(h, 1)) ------------------------------
+// The fp32 sibling of a bf16 model evaluates ONE U-Net pass per plan (the ill-conditioned leading reverse step); with
+// fp32 activations and TF32 operands on tcgen05 (conv_tc_kernel<BN, GW, true>) that pass costs a few bf16 steps' worth.
+// Layers whose channel counts are not multiples of 64 (the first conv, the head) stay on the SIMT kernel.
+int make_tmap_f32(dad_handle *h, CUtensorMap *m, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
+                  const cuuint32_t *box) {
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, base, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) DAD_FAIL(h, DAD_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed with CUresult %d", (int)r);
+  return DAD_OK;
+}
+
+bool setup_tc32_op(dad_handle *h, ConvOp &op) {
+  const ConvGeom &g = op.g;
+  if (op.head || g.C1 % 64 || g.C2 % 64 || g.L_out > TC_BM || TC_BM % g.L_out) return false;
+  if (!op.gname.empty()) {
+    const int gw = g.Cout / kGroups;
+    if (g.Cout % kGroups) return false;
+    if (gw == 8 && g.Cout == 64) { op.BN = 64; op.GW = 8; }
+    else if ((gw == 16 || gw == 32 || gw == 64 || gw == 128) && g.Cout % 128 == 0) { op.BN = 128; op.GW = gw; }
+    else if (gw == 256) { op.BN = 256; op.GW = 256; }
+    else return false;
+  } else {
+    op.GW = 0;
+    if (g.Cout % 128 == 0) op.BN = 128;
+    else if (g.Cout % 64 == 0) op.BN = 64;
+    else return false;
+  }
+  if (g.Cout % op.BN) return false;
+  ConvTcParams &p = op.tcp;
+  p = ConvTcParams{};
+  p.L_out = g.L_out;
+  p.out_mul = g.out_mul;
+  p.out_phase = g.out_phase;
+  p.Cout = g.Cout;
+  p.n_tiles_n = g.Cout / op.BN;
+  p.kch1 = g.C1 / 32;          // k blocks of 32 fp32 channels (one 128-byte swizzle row)
+  p.kch2 = g.C2 / 32;
+  p.taps = g.taps;
+  for (int t = 0; t < g.taps; ++t) {
+    const int s = g.in_stride, off = g.tap_off[t];
+    const int ph = ((off % s) + s) % s;
+    p.tap_p[t] = ph;
+    p.tap_j[t] = (off - ph) / s;
+  }
+  p.ls = h->d_ls;
+  return true;
+}
+
+int finish_tc32_op(dad_handle *h, ConvOp &op) {
+  const ConvGeom &g = op.g;
+  auto act_map = [&](CUtensorMap *m, int act) {
+    const Act &a = h->acts[act];
+    const int P = g.in_stride, J = a.L / P;
+    cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)P, (cuuint64_t)J, (cuuint64_t)h->cfg.max_batch};
+    cuuint64_t strides[3] = {(cuuint64_t)a.C * 4, (cuuint64_t)P * a.C * 4, (cuuint64_t)a.L * a.C * 4};
+    cuuint32_t box[4] = {32, 1, (cuuint32_t)g.L_out, (cuuint32_t)(TC_BM / g.L_out)};
+    return make_tmap_f32(h, m, act_ptr(h, act), 4, dims, strides, box);
+  };
+  int rc = act_map(&op.tmA1, op.in1);
+  if (rc) return rc;
+  if ((rc = act_map(&op.tmA2, op.in2 >= 0 ? op.in2 : op.in1))) return rc;
+  const cuuint64_t K = (cuuint64_t)g.taps * (g.C1 + g.C2);
+  cuuint64_t dims[2] = {K, (cuuint64_t)g.Cout};
+  cuuint64_t strides[1] = {K * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)op.BN};
+  if ((rc = make_tmap_f32(h, &op.tmW, op.w_k32, 2, dims, strides, box))) return rc;
+  ConvTcParams &p = op.tcp;
+  p.bias = op.bias;
+  p.gamma = op.gamma;
+  p.beta = op.beta;
+  p.ttab = op.tblock >= 0 ? h->tblocks[op.tblock].tab : nullptr;
+  p.residual = op.res >= 0 ? reinterpret_cast<const __nv_bfloat16 *>(act_ptr(h, op.res)) : nullptr;   // fp32 data (TF32 kernel)
+  p.out = act_ptr(h, op.out);
+  return DAD_OK;
+}
+
 // ---- v3 path ---------------------------------------------------------------------------------------
 int make_tmap_raw(dad_handle *h, CUtensorMap *m, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
                   const cuuint32_t *box, const char *what) {
@@ -930,6 +1013,15 @@ cudaError_t set_tc_attr(int max_optin) {
                               max_optin - (int)fa.sharedSizeBytes);
 }
 
+template <int BN, int GW>
+cudaError_t set_tc32_attr(int max_optin) {
+  cudaFuncAttributes fa{};
+  cudaError_t e = cudaFuncGetAttributes(&fa, conv_tc_kernel<BN, GW, true>);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(conv_tc_kernel<BN, GW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              max_optin - (int)fa.sharedSizeBytes);
+}
+
 // Opt-in shared memory sizes are set once at create (never inside a stream capture).
 int set_kernel_attrs(dad_handle *h) {
   CK(h, (set_tc_attr<64, 8>(h->max_smem_optin)));
@@ -942,6 +1034,14 @@ int set_kernel_attrs(dad_handle *h) {
   CK(h, (set_tc_attr<32, 0>(h->max_smem_optin)));
   CK(h, (set_tc_attr<64, 0>(h->max_smem_optin)));
   CK(h, (set_tc_attr<128, 0>(h->max_smem_optin)));
+  CK(h, (set_tc32_attr<64, 8>(h->max_smem_optin)));
+  CK(h, (set_tc32_attr<128, 16>(h->max_smem_optin)));
+  CK(h, (set_tc32_attr<128, 32>(h->max_smem_optin)));
+  CK(h, (set_tc32_attr<128, 64>(h->max_smem_optin)));
+  CK(h, (set_tc32_attr<128, 128>(h->max_smem_optin)));
+  CK(h, (set_tc32_attr<256, 256>(h->max_smem_optin)));
+  CK(h, (set_tc32_attr<64, 0>(h->max_smem_optin)));
+  CK(h, (set_tc32_attr<128, 0>(h->max_smem_optin)));
 #define T3_ATTR(gw, mh, mode, ns) CK(h, (set_t3_attr<gw, mh, mode, ns>(h->max_smem_optin)));
   T3_FOR_EACH(T3_ATTR)
 #undef T3_ATTR
@@ -1065,7 +1165,31 @@ int enqueue_tc(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
 }
 
 // ---- fp32 path ---------------------------------------------------------------------------------
+// One conv (+ GroupNorm + Mish + time bias + residual) of an fp32 handle on tcgen05 kind::tf32.
+int enqueue_tc32(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
+  ConvTcParams p = op.tcp;
+  p.B = B;
+  p.n_tiles_m = cdiv((long long)B * op.g.L_out, TC_BM);
+  const int tiles = p.n_tiles_m * p.n_tiles_n;
+  const int grid = std::min(tiles, h->sm_count);
+  bool ok = false;
+#define TC32_CASE(bn, gw)                                                                                                   \
+  if (op.BN == bn && op.GW == gw) {                                                                                         \
+    launch_k(conv_tc_kernel<bn, gw, true>, dim3((unsigned)grid), dim3(TC_THREADS), (size_t)TcCfg<bn>::smem_bytes(op.Cout_pad), \
+             st, 1, op.tmA1, op.tmA2, op.tmW, p);                                                                           \
+    ok = true;                                                                                                              \
+  }
+  TC32_CASE(64, 8) TC32_CASE(128, 16) TC32_CASE(128, 32) TC32_CASE(128, 64) TC32_CASE(128, 128) TC32_CASE(256, 256)
+  TC32_CASE(64, 0) TC32_CASE(128, 0)
+#undef TC32_CASE
+  if (!ok) DAD_FAIL(h, DAD_ERR_INVALID, "internal: no tf32 instantiation for BN=%d GW=%d", op.BN, op.GW);
+  h->counting += 1;
+  CK(h, cudaGetLastError());
+  return DAD_OK;
+}
+
 int enqueue_f32(dad_handle *h, const ConvOp &op, int B, cudaStream_t st) {
+  if (h->f32_math == 1 && op.tc32 && !h->rows_t) return enqueue_tc32(h, op, B, st);
   ConvF32Params p{};
   p.in1 = reinterpret_cast<const float *>(act_ptr(h, op.in1));
   p.in2 = op.in2 >= 0 ? reinterpret_cast<const float *>(act_ptr(h, op.in2)) : nullptr;
@@ -1455,7 +1579,7 @@ int dad_create(const dad_config *cfg, dad_handle **out) {
   h->elt = h->bf16 ? 2 : 4;
   h->time_dim = c.time_dim > 0 ? c.time_dim : c.dim;
   h->D = c.horizon * c.transition_dim;
-  if (h->bf16) {
+  {   // both precisions build tensor maps (fp32 handles for their TF32 tensor-core path)
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qr;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) {
@@ -1497,6 +1621,8 @@ int dad_create(const dad_config *cfg, dad_handle **out) {
     } else {
       op.Cout_pad = op.g.Cout;
       if ((rc = dev_alloc(h, &op.w_f32, (size_t)op.g.taps * op.Cin_store * op.g.Cout))) return fail(rc);
+      op.tc32 = setup_tc32_op(h, op);
+      if (op.tc32 && (rc = dev_alloc(h, &op.w_k32, (size_t)op.g.taps * op.Cin_store * op.g.Cout))) return fail(rc);
     }
     if ((rc = dev_alloc(h, &op.bias, (size_t)op.Cout_pad))) return fail(rc);
     fill_now(op.bias, 0, sizeof(float) * op.Cout_pad, h->own_stream);
@@ -1516,6 +1642,9 @@ int dad_create(const dad_config *cfg, dad_handle **out) {
       }
       setup_small_op(h, op);
     }
+  if (!h->bf16)
+    for (ConvOp &op : h->ops)
+      if (op.tc32 && (rc = finish_tc32_op(h, op))) return fail(rc);
   h->small_max_b = tuning_env("DAD_SMALL_MAX_B", h->small_max_b);
   if (h->bf16) {
     // tile-completion counters of the conv chains: one row per conv, one word per sample tile (>= 8 samples each)
@@ -1592,6 +1721,9 @@ int dad_load_weights(dad_handle *h, const dad_tensor *tensors, int32_t n) {
       const size_t total = (size_t)op.g.taps * op.Cin_real * op.g.Cout;
       pack_w_f32_kernel<<<cdiv(total, 256), 256, 0, st>>>(wd, op.w_f32, op.g.Cout, op.Cin_real, op.ksize, op.g.taps,
                                                           op.sel, op.transposed);
+      if (op.tc32)
+        pack_w_tf32_kmajor_kernel<<<cdiv(total, 256), 256, 0, st>>>(wd, op.w_k32, op.g.Cout, op.Cin_real, op.ksize, op.g.taps,
+                                                                    op.sel, op.transposed);
     }
     CK(h, cudaStreamSynchronize(st));   // `stage` is reused by the next tensor
     CK(h, copy_now(op.bias, b->data, sizeof(float) * op.g.Cout, h->own_stream));

@@ -526,6 +526,20 @@ __global__ void pack_w_f32_kernel(const float *__restrict__ w, float *__restrict
   out[idx] = transposed ? w[((size_t)c * Cout + n) * ksize + kk] : w[((size_t)n * Cin + c) * ksize + kk];
 }
 
+// Same source layouts -> fp32 K-major rows rounded to TF32 (round to nearest): Wk[n][t * Cin + c], the B operand of
+// conv_tc_kernel<BN, GW, true>.
+__global__ void pack_w_tf32_kmajor_kernel(const float *__restrict__ w, float *__restrict__ out, int Cout, int Cin,
+                                          int ksize, int taps, TapSel sel, int transposed) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)taps * Cin * Cout) return;
+  const int c = (int)(idx % Cin), t = (int)((idx / Cin) % taps), n = (int)(idx / ((size_t)Cin * taps));
+  const int kk = sel.k[t];
+  const float v = transposed ? w[((size_t)c * Cout + n) * ksize + kk] : w[((size_t)n * Cin + c) * ksize + kk];
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  out[idx] = __uint_as_float(r);
+}
+
 // Same source layouts -> bf16 K-major rows: Wb[n][t * Cin_pad + c], zero padded to (Cout_pad, Cin_pad).
 __global__ void pack_w_bf16_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ out, int Cout,
                                    int Cin, int Cout_pad, int Cin_pad, int ksize, int taps, TapSel sel,
