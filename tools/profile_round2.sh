@@ -42,7 +42,7 @@ python tools/summarize_ncu.py --out $O r02 halfcheetah conv_chain_kernel /tmp/r0
 timeout 400 ncu --set full --clock-control none -k regex:"conv_small" -s 60 -c 1 -f -o /tmp/r02_small python tools/layer_times.py pointmaze 1 > $O/r02_ncu6.log 2>&1
 python tools/summarize_ncu.py --out $O r02 pointmaze_b1 conv_small_kernel /tmp/r02_small.ncu-rep > /dev/null
 # the fp32 sibling's kernels (ill-conditioned leading step): TF32 mma.sync conv and the warp GroupNorm+Mish
-timeout 400 ncu --set full --clock-control none -k regex:"conv_tf32_kernel" -s 40 -c 2 -f -o /tmp/r02_tf32 $BC > $O/r02_ncu7.log 2>&1
-timeout 400 ncu --set full --clock-control none -k regex:"gn_mish_f32_warp" -s 30 -c 1 -f -o /tmp/r02_gnw $BC > $O/r02_ncu8.log 2>&1
-python tools/summarize_ncu.py --out $O r02 pointmaze_sibling conv_tf32_kernel /tmp/r02_tf32.ncu-rep gn_mish_f32_warp_kernel /tmp/r02_gnw.ncu-rep > /dev/null
+# (the sibling's convs are conv_tc_kernel<BN, GW, true>: the first conv_tc launches of a plan; bf16 conv_tc launches follow)
+timeout 400 ncu --set full --clock-control none -k regex:"conv_tc_kernel" -s 111 -c 12 -f -o /tmp/r02_tf32 $BC > $O/r02_ncu7.log 2>&1
+python tools/summarize_ncu.py --out $O r02 pointmaze_sibling conv_tc_kernel_tf32 /tmp/r02_tf32.ncu-rep > /dev/null
 du -sh $O; ls -la $O | head -40
